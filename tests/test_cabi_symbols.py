@@ -1,0 +1,54 @@
+"""The C-ABI library loads on a CPU-only host and exports every symbol that
+include/vqb200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import vq_gan_b200
+from vq_gan_b200 import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "vqb200.h")).read()
+    return sorted(set(re.findall(r"VQB_API\s+[\w\s\*]+?\b(vqb_\w+)\s*\(", text)))
+
+
+def test_header_declares_expected_surface():
+    names = declared_symbols()
+    for must in ("vqb_search_f32", "vqb_gather_loss_st_f32", "vqb_backward_f32", "vqb_hist_i64",
+                 "vqb_gather_f32", "vqb_codebook_prepare_f32", "vqb_last_error", "vqb_version"):
+        assert must in names
+    assert len(names) >= 17
+
+
+def test_library_exports_every_declared_symbol():
+    handle = ctypes.CDLL(_cabi.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(handle, name), f"{name} declared in vqb200.h but not exported"
+
+
+def test_python_prototypes_cover_header():
+    assert sorted(_cabi.PROTOTYPES) == declared_symbols()
+
+
+def test_version_and_size_queries_without_gpu():
+    lib = vq_gan_b200.lib()
+    assert lib.vqb_version() >= 100
+    # pure host arithmetic, no CUDA call
+    small = lib.vqb_codebook_pack_bytes(128, 256)
+    big = lib.vqb_codebook_pack_bytes(16384, 256)
+    assert 0 < small < big
+    assert lib.vqb_codebook_pack_bytes(0, 4) == 0
+    assert lib.vqb_tail_partials_bytes(1 << 20) >= 8 * (1 << 15)
+    assert lib.vqb_search_workspace_bytes(4, 32, 64, 128, 0) == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", "/nonexistent/libvqb200.so")
+    with pytest.raises(_cabi.VqbError, match="no CPU or eager fallback"):
+        _cabi.lib()

@@ -1,0 +1,70 @@
+"""Host-side logic of the drop-in that does not need a GPU."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden
+from vq_gan_b200 import VectorQuantizer
+from vq_gan_b200 import distributed as vdist
+
+
+def test_constructor_matches_reference_contract():
+    g = load_golden("init_seed42_k128_d256")
+    torch.manual_seed(42)
+    vq = VectorQuantizer(128, 256, 0.25)
+    # same codebook AND same RNG position afterwards as the reference constructor
+    np.testing.assert_array_equal(vq.embedding.weight.detach().numpy(), g["weight"])
+    np.testing.assert_array_equal(torch.rand(4).numpy(), g["next_rand"])
+    assert sorted(vq.state_dict().keys()) == list(g["state_keys"]) == ["embedding.weight"]
+    assert (vq.num_embeddings, vq.embedding_dim, vq.commitment_cost) == (128, 256, 0.25)
+    assert isinstance(vq.embedding, torch.nn.Embedding)
+
+
+def test_reference_checkpoint_loads_strictly():
+    vq = VectorQuantizer(16, 8)
+    sd = {"embedding.weight": torch.randn(16, 8)}
+    vq.load_state_dict(sd, strict=True)
+    assert torch.equal(vq.embedding.weight.detach(), sd["embedding.weight"])
+
+
+def test_cpu_inputs_are_rejected_not_emulated():
+    vq = VectorQuantizer(16, 4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        vq(torch.randn(1, 4, 2, 2))
+    with pytest.raises(RuntimeError):
+        vq.get_codebook_entry(torch.zeros(1, 2, 2, dtype=torch.int64))
+    with pytest.raises(RuntimeError):
+        vq.get_codebook_usage(torch.zeros(1, 2, 2, dtype=torch.int64))
+
+
+def test_shape_errors_like_reference():
+    vq = VectorQuantizer(16, 4)
+    with pytest.raises(RuntimeError):
+        vq(torch.randn(1, 5, 2, 2))  # reference: view(-1, 4) then matmul shape error
+    with pytest.raises(RuntimeError):
+        vq(torch.randn(4, 2, 2))
+    with pytest.raises(ValueError):
+        VectorQuantizer(16, 4, return_format="nope")
+
+
+def test_shard_range_covers_everything():
+    for total in (0, 1, 7, 64, 65536, 50000):
+        for world in (1, 2, 3, 8):
+            spans = [vdist.shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_stats_pack_roundtrip_is_exact_for_large_counts():
+    dE = torch.randn(5, 3)
+    hist = torch.tensor([0, 1, 4095, 4096, 1 << 20, (1 << 31) + 12345], dtype=torch.int64)
+    scal = torch.tensor([3.5, -1.0])
+    flat = vdist.pack_stats(dE, hist, scal)
+    a, s, h = vdist.unpack_stats(flat * 1.0, dE.shape, 2, hist.numel())
+    assert torch.equal(a, dE) and torch.equal(s, scal) and torch.equal(h, hist)
+    # summing R copies stays exact (what the all-reduce does)
+    a, s, h = vdist.unpack_stats(flat * 8.0, dE.shape, 2, hist.numel())
+    assert torch.equal(h, hist * 8)

@@ -1,0 +1,158 @@
+// C ABI: library plumbing, codebook pre-pass and search dispatch.
+#include <stdarg.h>
+#include <string.h>
+
+#include "vqb_common.cuh"
+
+namespace vqb {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return VQB_ERR_CUDA;
+}
+
+int sm_count() {
+    // immutable per-device capability cache
+    static int cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" int vqb_version(void) { return 100; }  // 0.1.0
+
+extern "C" const char* vqb_last_error(void) { return g_error; }
+
+extern "C" int vqb_device_query(int device, int* sm, int* cc_major, int* cc_minor, size_t* smem_optin) {
+    int v = 0;
+    if (sm) {
+        VQB_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+        *sm = v;
+    }
+    if (cc_major) {
+        VQB_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, device));
+        *cc_major = v;
+    }
+    if (cc_minor) {
+        VQB_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, device));
+        *cc_minor = v;
+    }
+    if (smem_optin) {
+        VQB_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        *smem_optin = (size_t)v;
+    }
+    return VQB_OK;
+}
+
+extern "C" size_t vqb_codebook_pack_bytes(int K, int D) {
+    if (K <= 0 || D <= 0) return 0;
+    return pack_layout(K, D).total;
+}
+
+extern "C" int vqb_codebook_prepare_f32(const float* E, int K, int D, void* pack, size_t pack_bytes,
+                                        vqb_stream_t stream) {
+    if (!E || !pack || K <= 0 || D <= 0) {
+        set_error("vqb_codebook_prepare_f32: invalid argument (K=%d D=%d)", K, D);
+        return VQB_ERR_INVALID_ARG;
+    }
+    if ((reinterpret_cast<uintptr_t>(pack) & 255u) != 0) {
+        set_error("vqb_codebook_prepare_f32: pack must be 256-byte aligned");
+        return VQB_ERR_INVALID_ARG;
+    }
+    const size_t need = pack_layout(K, D).total;
+    if (pack_bytes < need) {
+        set_error("codebook pack too small: %zu < %zu", pack_bytes, need);
+        return VQB_ERR_WORKSPACE;
+    }
+    return launch_codebook_prepare(E, K, D, pack, static_cast<cudaStream_t>(stream));
+}
+
+static int resolve_algo(int algo, int D) {
+    if (algo != VQB_ALGO_AUTO) return algo;
+    if (D <= kLowDMax) return VQB_ALGO_LOWD_FMA;
+    if (tc_eligible_dim(D)) return VQB_ALGO_TCGEN05;
+    return VQB_ALGO_FP32_TILE;
+}
+
+extern "C" size_t vqb_search_workspace_bytes(int64_t B, int D, int64_t HW, int K, int algo) {
+    if (B < 0 || HW < 0 || D <= 0 || K <= 0) return 0;
+    const int a = resolve_algo(algo, D);
+    if (a == VQB_ALGO_TCGEN05) return search_tc_workspace_bytes(B * HW, D, K);
+    return 0;
+}
+
+__global__ void write_stats_kernel(int64_t* stats, int64_t rescored, int64_t algo) {
+    stats[0] = rescored;
+    stats[1] = algo;
+    stats[2] = 0;
+    stats[3] = 0;
+}
+
+extern "C" int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
+                              const void* pack, int64_t* idx_out, float* dmin_out, void* workspace,
+                              size_t workspace_bytes, int algo, int64_t* stats_out, vqb_stream_t stream) {
+    if (B < 0 || HW < 0 || D <= 0 || K <= 0) {
+        set_error("vqb_search_f32: invalid shape B=%lld D=%d HW=%lld K=%d", (long long)B, D, (long long)HW, K);
+        return VQB_ERR_INVALID_ARG;
+    }
+    const int64_t N = B * HW;
+    if (N == 0) return VQB_OK;
+    if (!z || !E || !pack || !idx_out) {
+        set_error("vqb_search_f32: null pointer");
+        return VQB_ERR_INVALID_ARG;
+    }
+    if (N >= (1LL << 31)) {
+        set_error("vqb_search_f32: at most 2^31-1 tokens per call, got %lld", (long long)N);
+        return VQB_ERR_INVALID_ARG;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int a = resolve_algo(algo, D);
+    int rc;
+    switch (a) {
+        case VQB_ALGO_LOWD_FMA:
+            if (D > kLowDMax) {
+                set_error("VQB_ALGO_LOWD_FMA needs D <= %d, got %d", kLowDMax, D);
+                return VQB_ERR_UNSUPPORTED;
+            }
+            rc = launch_search_lowd(z, B, D, HW, K, pack, idx_out, dmin_out, s);
+            break;
+        case VQB_ALGO_FP32_TILE:
+            rc = launch_search_fp32(z, B, D, HW, E, K, pack, nullptr, nullptr, 0, idx_out, dmin_out, s);
+            break;
+        case VQB_ALGO_TCGEN05:
+            if (!tc_eligible_dim(D)) {
+                set_error("VQB_ALGO_TCGEN05 needs D %% 64 == 0 and %d <= D <= %d, got %d", kTcMinD, kTcMaxD, D);
+                return VQB_ERR_UNSUPPORTED;
+            }
+            // writes its own stats (re-scored token count is only known on the device)
+            return launch_search_tc(z, B, D, HW, E, K, pack, idx_out, dmin_out, workspace, workspace_bytes,
+                                    stats_out, s);
+        default:
+            set_error("vqb_search_f32: unknown algo %d", algo);
+            return VQB_ERR_INVALID_ARG;
+    }
+    if (rc != VQB_OK) return rc;
+    if (stats_out) {
+        write_stats_kernel<<<1, 1, 0, s>>>(stats_out, 0, a);
+        VQB_LAUNCH_CHECK("write_stats_kernel");
+    }
+    return VQB_OK;
+}

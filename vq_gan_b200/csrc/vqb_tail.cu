@@ -1,0 +1,600 @@
+// HBM-bound kernels either side of the search: forward tail (gather + loss +
+// straight-through), backward (dz + dE scatter + histogram), get_codebook_entry,
+// get_codebook_usage, and the EMA / sharded-argmin extensions.
+// Reference lines: quantizer.py:80-98 (tail), autograd of :89-98 (backward),
+// :112-132 (entry), :134-149 (usage).
+//
+// Common mapping: the latent is z[B, D, HW]; a CTA is TX tokens (x, fastest) by
+// S channel slices (y), TX*S = 256, so every global access to z / z_q / dz / g is
+// a coalesced run along HW and every codebook access is a float4 walk along one
+// row (rows are L2-resident: K*D*4 <= 64 MiB).
+#include "vqb_common.cuh"
+
+namespace vqb {
+
+constexpr int kTailThreads = 256;
+
+struct TailShape {
+    int tx, slices, dims_per_slice;
+};
+
+static TailShape tail_shape(int D) {
+    TailShape s;
+    int slices = 1;
+    // keep every slice a whole number of float4 groups so the vector path stays aligned
+    if (D % 4 == 0)
+        while (slices < 8 && D % (slices * 8) == 0) slices *= 2;
+    s.slices = slices;
+    s.tx = kTailThreads / slices;
+    s.dims_per_slice = D / slices;
+    return s;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+                 "f"(d)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// forward tail
+// ---------------------------------------------------------------------------
+template <bool kVec4>
+__global__ void __launch_bounds__(kTailThreads)
+    gather_loss_st_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                          const int64_t* __restrict__ idx, int64_t N, int D, int64_t HW, int K,
+                          int dims_per_slice, float* __restrict__ zq_out,
+                          double* __restrict__ partials, int* __restrict__ err_flag) {
+    const int64_t tok = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int d0 = threadIdx.y * dims_per_slice;
+    float sq = 0.f;
+    if (tok < N) {
+        int64_t k = idx[tok];
+        if (k < 0 || k >= K) {
+            if (err_flag) *err_flag = 1;
+            k = 0;
+        }
+        const int64_t b = tok / HW;
+        const int64_t off = (b * D) * HW + (tok - b * HW);
+        const float* erow = E + (size_t)k * D;
+        if constexpr (kVec4) {
+            for (int d = d0; d < d0 + dims_per_slice; d += 4) {
+                const float4 ev = __ldg(reinterpret_cast<const float4*>(erow + d));
+                const float e[4] = {ev.x, ev.y, ev.z, ev.w};
+                float zv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) zv[j] = __ldg(z + off + (int64_t)(d + j) * HW);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float diff = __fsub_rn(e[j], zv[j]);
+                    zq_out[off + (int64_t)(d + j) * HW] = __fadd_rn(zv[j], diff);
+                    sq = fmaf(diff, diff, sq);
+                }
+            }
+        } else {
+            for (int d = d0; d < d0 + dims_per_slice; ++d) {
+                const float ev = __ldg(erow + d);
+                const float zv = __ldg(z + off + (int64_t)d * HW);
+                const float diff = __fsub_rn(ev, zv);
+                zq_out[off + (int64_t)d * HW] = __fadd_rn(zv, diff);
+                sq = fmaf(diff, diff, sq);
+            }
+        }
+    }
+    // block reduction in double, one partial per CTA (fixed order -> deterministic)
+    __shared__ double warp_part[kTailThreads / 32];
+    const int lin = threadIdx.y * blockDim.x + threadIdx.x;
+    double v = warp_sum_f64((double)sq);
+    if ((lin & 31) == 0) warp_part[lin >> 5] = v;
+    __syncthreads();
+    if (lin == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kTailThreads / 32; ++w) s += warp_part[w];
+        partials[blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    loss_finalize_kernel(const double* __restrict__ partials, int64_t n_partials, double inv_n,
+                         float beta, float* __restrict__ loss_out) {
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n_partials; i += 256) s += partials[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float mse = (float)(sh[0] * inv_n);
+        loss_out[0] = mse;
+        loss_out[1] = __fadd_rn(mse, __fmul_rn(beta, mse));  // fl(cb + fl(beta*commit)), quantizer.py:95
+    }
+}
+
+// ---------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------
+template <bool kVec4>
+__global__ void __launch_bounds__(kTailThreads)
+    backward_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                    const int64_t* __restrict__ idx, const float* __restrict__ g_zq,
+                    const float* __restrict__ g_vq, float beta, float norm, int64_t N, int D,
+                    int64_t HW, int K, int dims_per_slice, float* __restrict__ dz_out,
+                    float* __restrict__ dE, unsigned long long* __restrict__ hist) {
+    const int64_t tok = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int d0 = threadIdx.y * dims_per_slice;
+    const float gv = g_vq ? __ldg(g_vq) : 0.f;
+    const float gbeta = __fmul_rn(gv, beta);
+    const bool live = tok < N;
+    int64_t k = 0;
+    if (live) {
+        k = idx[tok];
+        if (k < 0 || k >= K) k = 0;
+    }
+    if (hist != nullptr && threadIdx.y == 0) {
+        // warp-aggregated histogram: one atomic per distinct code per warp
+        const unsigned active = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const unsigned peers = __match_any_sync(active, (int)k);
+            if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(hist + k, (unsigned long long)__popc(peers));
+        }
+    }
+    if (!live) return;
+    const int64_t b = tok / HW;
+    const int64_t off = (b * D) * HW + (tok - b * HW);
+    const float* erow = E + (size_t)k * D;
+    float* drow = dE + (size_t)k * D;
+    if constexpr (kVec4) {
+        for (int d = d0; d < d0 + dims_per_slice; d += 4) {
+            const float4 ev = __ldg(reinterpret_cast<const float4*>(erow + d));
+            const float e[4] = {ev.x, ev.y, ev.z, ev.w};
+            float zv[4], gz[4], c[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                zv[j] = __ldg(z + off + (int64_t)(d + j) * HW);
+                gz[j] = g_zq ? __ldg(g_zq + off + (int64_t)(d + j) * HW) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float t = __fmul_rn(__fmul_rn(norm, __fsub_rn(zv[j], e[j])), gv);
+                dz_out[off + (int64_t)(d + j) * HW] = __fadd_rn(gz[j], t);
+                c[j] = __fmul_rn(__fmul_rn(norm, __fsub_rn(e[j], zv[j])), gbeta);
+            }
+            if (dE) red_add_v4(drow + d, c[0], c[1], c[2], c[3]);
+        }
+    } else {
+        for (int d = d0; d < d0 + dims_per_slice; ++d) {
+            const float ev = __ldg(erow + d);
+            const float zv = __ldg(z + off + (int64_t)d * HW);
+            const float gz = g_zq ? __ldg(g_zq + off + (int64_t)d * HW) : 0.f;
+            const float t = __fmul_rn(__fmul_rn(norm, __fsub_rn(zv, ev)), gv);
+            dz_out[off + (int64_t)d * HW] = __fadd_rn(gz, t);
+            if (dE) atomicAdd(drow + d, __fmul_rn(__fmul_rn(norm, __fsub_rn(ev, zv)), gbeta));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// get_codebook_entry
+// ---------------------------------------------------------------------------
+template <bool kVec4>
+__global__ void __launch_bounds__(kTailThreads)
+    gather_kernel(const float* __restrict__ E, const int64_t* __restrict__ idx, int64_t N, int D,
+                  int64_t HW, int K, int dims_per_slice, float* __restrict__ out,
+                  int* __restrict__ err_flag) {
+    const int64_t tok = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tok >= N) return;
+    const int d0 = threadIdx.y * dims_per_slice;
+    int64_t k = idx[tok];
+    if (k < 0 || k >= K) {
+        if (err_flag) *err_flag = 1;
+        k = 0;
+    }
+    const int64_t b = tok / HW;
+    const int64_t off = (b * D) * HW + (tok - b * HW);
+    const float* erow = E + (size_t)k * D;
+    if constexpr (kVec4) {
+        for (int d = d0; d < d0 + dims_per_slice; d += 4) {
+            const float4 ev = __ldg(reinterpret_cast<const float4*>(erow + d));
+            out[off + (int64_t)(d + 0) * HW] = ev.x;
+            out[off + (int64_t)(d + 1) * HW] = ev.y;
+            out[off + (int64_t)(d + 2) * HW] = ev.z;
+            out[off + (int64_t)(d + 3) * HW] = ev.w;
+        }
+    } else {
+        for (int d = d0; d < d0 + dims_per_slice; ++d) out[off + (int64_t)d * HW] = __ldg(erow + d);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// get_codebook_usage
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    hist_kernel(const int64_t* __restrict__ idx, int64_t N, int K, unsigned long long* __restrict__ hist,
+                int* __restrict__ err_flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < N; base += stride) {
+        const int64_t i = base + threadIdx.x;
+        const bool live = i < N;
+        int64_t k = live ? idx[i] : 0;
+        bool ok = live;
+        if (live && (k < 0 || k >= K)) {
+            if (err_flag) *err_flag = 1;
+            ok = false;
+        }
+        const unsigned active = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const unsigned peers = __match_any_sync(active, (int)k);
+            if ((threadIdx.x & 31) == __ffs(peers) - 1)
+                atomicAdd(hist + k, (unsigned long long)__popc(peers));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    count_used_kernel(const unsigned long long* __restrict__ hist, int K,
+                      unsigned long long* __restrict__ used) {
+    int c = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x)
+        c += hist[k] != 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(used, (unsigned long long)c);
+}
+
+// ---------------------------------------------------------------------------
+// extensions
+// ---------------------------------------------------------------------------
+template <bool kVec4>
+__global__ void __launch_bounds__(kTailThreads)
+    code_sums_kernel(const float* __restrict__ z, const int64_t* __restrict__ idx, int64_t N, int D,
+                     int64_t HW, int K, int dims_per_slice, float* __restrict__ counts,
+                     float* __restrict__ sums) {
+    const int64_t tok = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int d0 = threadIdx.y * dims_per_slice;
+    const bool live = tok < N;
+    int64_t k = 0;
+    if (live) {
+        k = idx[tok];
+        if (k < 0 || k >= K) k = 0;
+    }
+    if (threadIdx.y == 0) {
+        const unsigned active = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const unsigned peers = __match_any_sync(active, (int)k);
+            if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counts + k, (float)__popc(peers));
+        }
+    }
+    if (!live) return;
+    const int64_t b = tok / HW;
+    const int64_t off = (b * D) * HW + (tok - b * HW);
+    float* srow = sums + (size_t)k * D;
+    if constexpr (kVec4) {
+        for (int d = d0; d < d0 + dims_per_slice; d += 4) {
+            float zv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) zv[j] = __ldg(z + off + (int64_t)(d + j) * HW);
+            red_add_v4(srow + d, zv[0], zv[1], zv[2], zv[3]);
+        }
+    } else {
+        for (int d = d0; d < d0 + dims_per_slice; ++d)
+            atomicAdd(srow + d, __ldg(z + off + (int64_t)d * HW));
+    }
+}
+
+__global__ void ema_sizes_kernel(float* __restrict__ cluster_size, const float* __restrict__ counts,
+                                 int K, float decay, float* __restrict__ total) {
+    float part = 0.f;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+        const float v = cluster_size[k] * decay + counts[k] * (1.f - decay);
+        cluster_size[k] = v;
+        part += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(total, part);
+}
+
+__global__ void ema_embed_kernel(float* __restrict__ E, const float* __restrict__ cluster_size,
+                                 float* __restrict__ embed_sum, const float* __restrict__ sums, int K,
+                                 int D, float decay, float eps, const float* __restrict__ total) {
+    const size_t n = (size_t)K * D;
+    const float tot = *total;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i / D);
+        const float m = embed_sum[i] * decay + sums[i] * (1.f - decay);
+        embed_sum[i] = m;
+        const float smoothed = (cluster_size[k] + eps) / (tot + K * eps) * tot;
+        E[i] = m / smoothed;
+    }
+}
+
+__global__ void pack_keys_kernel(const float* __restrict__ dmin, const int64_t* __restrict__ idx,
+                                 int64_t n, int64_t index_offset, int64_t* __restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int bits = __float_as_int(dmin[i]);
+    if (bits < 0) bits ^= 0x7fffffff;  // monotone signed order of IEEE floats
+    keys[i] = ((int64_t)bits << 32) | (int64_t)(uint32_t)(idx[i] + index_offset);
+}
+
+__global__ void unpack_keys_kernel(const int64_t* __restrict__ keys, int64_t n,
+                                   int64_t* __restrict__ idx_out, float* __restrict__ dmin_out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t key = keys[i];
+    idx_out[i] = (int64_t)(uint32_t)(key & 0xffffffffll);
+    if (dmin_out) {
+        int bits = (int)(key >> 32);
+        if (bits < 0) bits ^= 0x7fffffff;
+        dmin_out[i] = __int_as_float(bits);
+    }
+}
+
+// FP32 FMA peak: 16 independent chains per thread, operands from registers
+template <bool kPacked>
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float a, float b, float* sink) {
+    if constexpr (kPacked) {
+        unsigned long long x[8];
+        const unsigned long long a2 = pack_f32x2(a, a + 1e-3f), b2 = pack_f32x2(b, b - 1e-3f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = pack_f32x2(threadIdx.x * 1e-3f + i, i * 0.5f);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = fma_f32x2(x[i], a2, b2);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float lo, hi;
+            unpack_f32x2(x[i], lo, hi);
+            s += lo + hi;
+        }
+        if (s == 123.456f) sink[0] = s;
+    } else {
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = threadIdx.x * 1e-3f + i;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = fmaf(x[i], a, b);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += x[i];
+        if (s == 123.456f) sink[0] = s;
+    }
+}
+
+}  // namespace vqb
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace vqb;
+
+static bool vec4_ok(int D, const void* E) {
+    return (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(E) & 15u) == 0);
+}
+
+static int check_shape(int64_t B, int D, int64_t HW, int K) {
+    if (B < 0 || HW < 0 || D <= 0 || K <= 0) {
+        set_error("invalid shape B=%lld D=%d HW=%lld K=%d", (long long)B, D, (long long)HW, K);
+        return VQB_ERR_INVALID_ARG;
+    }
+    return VQB_OK;
+}
+
+extern "C" size_t vqb_tail_partials_bytes(int64_t n_tokens) {
+    return sizeof(double) * (size_t)((n_tokens + 31) / 32 + 1);
+}
+
+extern "C" int vqb_gather_loss_st_f32(const float* z, const float* E, const int64_t* idx, int64_t B,
+                                      int D, int64_t HW, int K, float beta, float* zq_out,
+                                      float* loss_out, void* partials, size_t partials_bytes,
+                                      int* err_flag, vqb_stream_t stream) {
+    if (int rc = check_shape(B, D, HW, K)) return rc;
+    if (!z || !E || !idx || !zq_out || !loss_out || !partials) {
+        set_error("vqb_gather_loss_st_f32: null pointer");
+        return VQB_ERR_INVALID_ARG;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t N = B * HW;
+    const TailShape sh = tail_shape(D);
+    const int64_t blocks = (N + sh.tx - 1) / sh.tx;
+    if (partials_bytes < sizeof(double) * (size_t)(blocks + 1)) {
+        set_error("partials scratch too small: %zu < %zu", partials_bytes,
+                  sizeof(double) * (size_t)(blocks + 1));
+        return VQB_ERR_WORKSPACE;
+    }
+    if (N == 0) {
+        VQB_CUDA_TRY(cudaMemsetAsync(loss_out, 0xff, 2 * sizeof(float), s));  // NaN like mean of empty
+        return VQB_OK;
+    }
+    const dim3 block(sh.tx, sh.slices);
+    double* parts = static_cast<double*>(partials);
+    if (vec4_ok(D, E))
+        gather_loss_st_kernel<true><<<(unsigned)blocks, block, 0, s>>>(
+            z, E, idx, N, D, HW, K, sh.dims_per_slice, zq_out, parts, err_flag);
+    else
+        gather_loss_st_kernel<false><<<(unsigned)blocks, block, 0, s>>>(
+            z, E, idx, N, D, HW, K, sh.dims_per_slice, zq_out, parts, err_flag);
+    VQB_LAUNCH_CHECK("gather_loss_st_kernel");
+    loss_finalize_kernel<<<1, 256, 0, s>>>(parts, blocks, 1.0 / ((double)N * D), beta, loss_out);
+    VQB_LAUNCH_CHECK("loss_finalize_kernel");
+    return VQB_OK;
+}
+
+extern "C" int vqb_backward_f32(const float* z, const float* E, const int64_t* idx, const float* g_zq,
+                                const float* g_vq, float beta, int64_t B, int D, int64_t HW, int K,
+                                float* dz_out, float* dE_accum, int64_t* hist_accum,
+                                vqb_stream_t stream) {
+    if (int rc = check_shape(B, D, HW, K)) return rc;
+    if (!z || !E || !idx || !dz_out) {
+        set_error("vqb_backward_f32: null pointer");
+        return VQB_ERR_INVALID_ARG;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t N = B * HW;
+    if (N == 0) return VQB_OK;
+    const TailShape sh = tail_shape(D);
+    const int64_t blocks = (N + sh.tx - 1) / sh.tx;
+    const dim3 block(sh.tx, sh.slices);
+    const float norm = (float)(2.0 / ((double)N * D));
+    unsigned long long* hist = reinterpret_cast<unsigned long long*>(hist_accum);
+    const bool v4 = vec4_ok(D, E) && (!dE_accum || (reinterpret_cast<uintptr_t>(dE_accum) & 15u) == 0);
+    if (v4)
+        backward_kernel<true><<<(unsigned)blocks, block, 0, s>>>(
+            z, E, idx, g_zq, g_vq, beta, norm, N, D, HW, K, sh.dims_per_slice, dz_out, dE_accum, hist);
+    else
+        backward_kernel<false><<<(unsigned)blocks, block, 0, s>>>(
+            z, E, idx, g_zq, g_vq, beta, norm, N, D, HW, K, sh.dims_per_slice, dz_out, dE_accum, hist);
+    VQB_LAUNCH_CHECK("backward_kernel");
+    return VQB_OK;
+}
+
+extern "C" int vqb_gather_f32(const float* E, const int64_t* idx, int64_t B, int D, int64_t HW, int K,
+                              float* out, int* err_flag, vqb_stream_t stream) {
+    if (int rc = check_shape(B, D, HW, K)) return rc;
+    if (!E || !idx || !out) {
+        set_error("vqb_gather_f32: null pointer");
+        return VQB_ERR_INVALID_ARG;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t N = B * HW;
+    if (N == 0) return VQB_OK;
+    const TailShape sh = tail_shape(D);
+    const int64_t blocks = (N + sh.tx - 1) / sh.tx;
+    const dim3 block(sh.tx, sh.slices);
+    if (vec4_ok(D, E))
+        gather_kernel<true><<<(unsigned)blocks, block, 0, s>>>(E, idx, N, D, HW, K, sh.dims_per_slice,
+                                                              out, err_flag);
+    else
+        gather_kernel<false><<<(unsigned)blocks, block, 0, s>>>(E, idx, N, D, HW, K, sh.dims_per_slice,
+                                                               out, err_flag);
+    VQB_LAUNCH_CHECK("gather_kernel");
+    return VQB_OK;
+}
+
+extern "C" int vqb_hist_i64(const int64_t* idx, int64_t n_tokens, int K, int64_t* hist_out,
+                            int64_t* used_out, int* err_flag, vqb_stream_t stream) {
+    if (n_tokens < 0 || K <= 0 || !hist_out || (!idx && n_tokens > 0)) {
+        set_error("vqb_hist_i64: invalid argument");
+        return VQB_ERR_INVALID_ARG;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VQB_CUDA_TRY(cudaMemsetAsync(hist_out, 0, sizeof(int64_t) * (size_t)K, s));
+    if (used_out) VQB_CUDA_TRY(cudaMemsetAsync(used_out, 0, sizeof(int64_t), s));
+    unsigned long long* hist = reinterpret_cast<unsigned long long*>(hist_out);
+    if (n_tokens > 0) {
+        int64_t blocks = (n_tokens + 255) / 256;
+        const int64_t cap = (int64_t)sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        hist_kernel<<<(unsigned)blocks, 256, 0, s>>>(idx, n_tokens, K, hist, err_flag);
+        VQB_LAUNCH_CHECK("hist_kernel");
+    }
+    if (used_out) {
+        int blocks = (K + 255) / 256;
+        if (blocks > 1024) blocks = 1024;
+        count_used_kernel<<<blocks, 256, 0, s>>>(hist, K, reinterpret_cast<unsigned long long*>(used_out));
+        VQB_LAUNCH_CHECK("count_used_kernel");
+    }
+    return VQB_OK;
+}
+
+extern "C" int vqb_code_sums_f32(const float* z, const int64_t* idx, int64_t B, int D, int64_t HW, int K,
+                                 float* counts_accum, float* sums_accum, vqb_stream_t stream) {
+    if (int rc = check_shape(B, D, HW, K)) return rc;
+    if (!z || !idx || !counts_accum || !sums_accum) {
+        set_error("vqb_code_sums_f32: null pointer");
+        return VQB_ERR_INVALID_ARG;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t N = B * HW;
+    if (N == 0) return VQB_OK;
+    const TailShape sh = tail_shape(D);
+    const int64_t blocks = (N + sh.tx - 1) / sh.tx;
+    const dim3 block(sh.tx, sh.slices);
+    if (vec4_ok(D, sums_accum))
+        code_sums_kernel<true><<<(unsigned)blocks, block, 0, s>>>(z, idx, N, D, HW, K, sh.dims_per_slice,
+                                                                 counts_accum, sums_accum);
+    else
+        code_sums_kernel<false><<<(unsigned)blocks, block, 0, s>>>(z, idx, N, D, HW, K, sh.dims_per_slice,
+                                                                  counts_accum, sums_accum);
+    VQB_LAUNCH_CHECK("code_sums_kernel");
+    return VQB_OK;
+}
+
+extern "C" int vqb_ema_update_f32(float* E, float* cluster_size, float* embed_sum, const float* counts,
+                                  const float* sums, int K, int D, float decay, float eps,
+                                  float* total_scratch, vqb_stream_t stream) {
+    if (K <= 0 || D <= 0 || !E || !cluster_size || !embed_sum || !counts || !sums || !total_scratch) {
+        set_error("vqb_ema_update_f32: invalid argument");
+        return VQB_ERR_INVALID_ARG;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VQB_CUDA_TRY(cudaMemsetAsync(total_scratch, 0, sizeof(float), s));
+    int blocks = (K + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    ema_sizes_kernel<<<blocks, 256, 0, s>>>(cluster_size, counts, K, decay, total_scratch);
+    VQB_LAUNCH_CHECK("ema_sizes_kernel");
+    size_t n = (size_t)K * D;
+    size_t b2 = (n + 255) / 256;
+    if (b2 > (size_t)sm_count() * 16) b2 = (size_t)sm_count() * 16;
+    ema_embed_kernel<<<(unsigned)b2, 256, 0, s>>>(E, cluster_size, embed_sum, sums, K, D, decay, eps,
+                                                  total_scratch);
+    VQB_LAUNCH_CHECK("ema_embed_kernel");
+    return VQB_OK;
+}
+
+extern "C" int vqb_pack_argmin_keys(const float* dmin, const int64_t* idx, int64_t n,
+                                    int64_t index_offset, int64_t* keys_out, vqb_stream_t stream) {
+    if (n < 0 || (n > 0 && (!dmin || !idx || !keys_out))) {
+        set_error("vqb_pack_argmin_keys: invalid argument");
+        return VQB_ERR_INVALID_ARG;
+    }
+    if (n == 0) return VQB_OK;
+    pack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dmin, idx, n, index_offset, keys_out);
+    VQB_LAUNCH_CHECK("pack_keys_kernel");
+    return VQB_OK;
+}
+
+extern "C" int vqb_unpack_argmin_keys(const int64_t* keys, int64_t n, int64_t* idx_out, float* dmin_out,
+                                      vqb_stream_t stream) {
+    if (n < 0 || (n > 0 && (!keys || !idx_out))) {
+        set_error("vqb_unpack_argmin_keys: invalid argument");
+        return VQB_ERR_INVALID_ARG;
+    }
+    if (n == 0) return VQB_OK;
+    unpack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        keys, n, idx_out, dmin_out);
+    VQB_LAUNCH_CHECK("unpack_keys_kernel");
+    return VQB_OK;
+}
+
+extern "C" int vqb_fma_peak_launch(int packed, int iters, float* sink, double* flops_host,
+                                   vqb_stream_t stream) {
+    if (iters <= 0 || !sink) {
+        set_error("vqb_fma_peak_launch: invalid argument");
+        return VQB_ERR_INVALID_ARG;
+    }
+    const int blocks = sm_count() * 8;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (packed)
+        fma_peak_kernel<true><<<blocks, 256, 0, s>>>(iters, 0.999f, 0.001f, sink);
+    else
+        fma_peak_kernel<false><<<blocks, 256, 0, s>>>(iters, 0.999f, 0.001f, sink);
+    VQB_LAUNCH_CHECK("fma_peak_kernel");
+    // per thread per iteration: 8 rounds x 16 lanes of FMA = 128 FMA = 256 flop
+    if (flops_host) *flops_host = 256.0 * iters * 256.0 * blocks;
+    return VQB_OK;
+}

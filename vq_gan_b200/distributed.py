@@ -1,0 +1,91 @@
+"""Multi-GPU modes of the VQ bottleneck (one process per GPU, torch.distributed).
+
+Data parallel (the reference's mode: accelerate -> DDP, train_vqgan.py:111-114,
+197-209): tokens are sharded, the codebook is replicated, and the per-step
+codebook statistics -- dE[K,D], the usage histogram and the squared-error sum --
+are summed over ranks in ONE fp32 all-reduce (NCCL over NVLink on B200).  The
+histogram rides in the same message as two exactly-summable fp32 planes
+(count mod 4096, count div 4096).
+
+Codebook sharded (extension for very large K): every rank searches its slice
+of the codebook for ALL tokens, packs (distance, global index) into an ordered
+int64 key and a MIN all-reduce picks the nearest code, lowest index on ties.
+
+The collectives are backend-agnostic torch.distributed calls, so the host logic
+is testable with gloo on CPU; the kernels either side are CUDA-only.
+"""
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+_HIST_RADIX = 4096
+
+
+def shard_range(total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous near-equal split of `total` items; first `total % world` ranks get one more."""
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def pack_stats(dE: torch.Tensor, hist: Optional[torch.Tensor], scalars: Optional[torch.Tensor]
+               ) -> torch.Tensor:
+    """[dE | scalars | hist mod R | hist div R] as one flat fp32 buffer."""
+    parts = [dE.reshape(-1).float()]
+    if scalars is not None:
+        parts.append(scalars.reshape(-1).float())
+    if hist is not None:
+        h = hist.reshape(-1).long()
+        parts.append((h % _HIST_RADIX).float())
+        parts.append(torch.div(h, _HIST_RADIX, rounding_mode="floor").float())
+    return torch.cat(parts)
+
+
+def unpack_stats(flat: torch.Tensor, dE_shape, n_scalars: int, n_hist: int):
+    k = 1
+    for s in dE_shape:
+        k *= int(s)
+    dE = flat[:k].reshape(dE_shape)
+    scalars = flat[k:k + n_scalars] if n_scalars else None
+    hist = None
+    if n_hist:
+        lo = flat[k + n_scalars:k + n_scalars + n_hist]
+        hi = flat[k + n_scalars + n_hist:k + n_scalars + 2 * n_hist]
+        hist = lo.round().long() + hi.round().long() * _HIST_RADIX
+    return dE, scalars, hist
+
+
+def allreduce_stats(dE: torch.Tensor, hist: Optional[torch.Tensor] = None,
+                    scalars: Optional[torch.Tensor] = None, group=None, average_dE: bool = True):
+    """Sum-all-reduce of the codebook statistics in one message.
+
+    `average_dE=True` reproduces DDP, which AVERAGES gradients over ranks while
+    every rank normalises its loss by its local n; the histogram
+    and scalars are always summed.  Exact for world sizes up to 4096."""
+    world = dist.get_world_size(group)
+    flat = pack_stats(dE, hist, scalars)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    out_dE, out_scalars, out_hist = unpack_stats(
+        flat, dE.shape, 0 if scalars is None else scalars.numel(), 0 if hist is None else hist.numel())
+    if average_dE:
+        out_dE = out_dE / world
+    return out_dE, out_hist, out_scalars
+
+
+def reduce_argmin_keys(keys: torch.Tensor, group=None) -> torch.Tensor:
+    """MIN all-reduce of packed (distance, index) keys (in place)."""
+    dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+    return keys
+
+
+def sharded_search(z: torch.Tensor, weight_shard: torch.Tensor, index_offset: int, group=None,
+                   algo: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Codebook-sharded nearest-code search.  `z` is the SAME token batch on every
+    rank of `group`; `weight_shard` is this rank's rows [index_offset, index_offset+K_r)
+    of the global codebook.  Returns (global indices, min score) on every rank."""
+    from . import ops
+    idx, dmin, _ = ops.search(z, weight_shard, algo)
+    keys = ops.pack_argmin_keys(dmin, idx, int(index_offset))
+    reduce_argmin_keys(keys, group)
+    return ops.unpack_argmin_keys(keys)

@@ -1,0 +1,312 @@
+"""torch.library custom ops over the C ABI (`vqb200::*`).
+
+PyTorch is the tensor / stream / autograd carrier only: every op validates its
+arguments, allocates outputs with torch, and enqueues libvqb200 kernels on the
+current CUDA stream.  CPU tensors are rejected -- there is no fallback path.
+"""
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+from ._cabi import check, lib
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda_f32(t: Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"vq_gan_b200: `{name}` must be a CUDA tensor (got {t.device}); "
+                           "this package has no CPU path")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"vq_gan_b200: `{name}` must be float32, got {t.dtype}")
+
+
+def _shape_bdhw(z: Tensor, weight: Tensor) -> Tuple[int, int, int, int]:
+    if z.dim() < 2:
+        raise RuntimeError(f"latent must be [B, D, ...], got {tuple(z.shape)}")
+    B, D = int(z.shape[0]), int(z.shape[1])
+    if weight.dim() != 2 or int(weight.shape[1]) != D:
+        # the reference fails in `z.view(-1, embedding_dim)` / matmul for the same input
+        raise RuntimeError(f"latent channels ({D}) do not match the codebook {tuple(weight.shape)}")
+    HW = 1
+    for s in z.shape[2:]:
+        HW *= int(s)
+    return B, D, HW, int(weight.shape[0])
+
+
+def _bytes(n: int, device) -> Tensor:
+    return torch.empty(max(int(n), 1), dtype=torch.uint8, device=device)
+
+
+def _prepare(weight: Tensor) -> Tensor:
+    K, D = int(weight.shape[0]), int(weight.shape[1])
+    nbytes = lib().vqb_codebook_pack_bytes(K, D)
+    pack = _bytes(nbytes, weight.device)
+    check(lib().vqb_codebook_prepare_f32(_p(weight), K, D, _p(pack), nbytes, _stream()),
+          "vqb_codebook_prepare_f32")
+    return pack
+
+
+def _search_into(z: Tensor, weight: Tensor, algo: int, want_dmin: bool):
+    B, D, HW, K = _shape_bdhw(z, weight)
+    dev = z.device
+    pack = _prepare(weight)
+    idx = torch.empty((B,) + tuple(z.shape[2:]), dtype=torch.int64, device=dev)
+    dmin = torch.empty(idx.shape, dtype=torch.float32, device=dev) if want_dmin else None
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    ws_bytes = lib().vqb_search_workspace_bytes(B, D, HW, K, algo)
+    ws = _bytes(ws_bytes, dev)
+    check(lib().vqb_search_f32(_p(z), B, D, HW, _p(weight), K, _p(pack), _p(idx), _p(dmin), _p(ws),
+                               ws_bytes, algo, _p(stats), _stream()), "vqb_search_f32")
+    return idx, dmin, stats
+
+
+# ---------------------------------------------------------------------------
+# search only (encode_to_indices-style bulk use; quantizer.py:68-76)
+# ---------------------------------------------------------------------------
+@torch.library.custom_op("vqb200::search", mutates_args=())
+def search(z: Tensor, weight: Tensor, algo: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
+    """(indices[B,*spatial] int64, dmin[B,*spatial] f32, stats int64[4])."""
+    _need_cuda_f32(z, "z")
+    _need_cuda_f32(weight, "weight")
+    z = z.contiguous()
+    weight = weight.contiguous()
+    with torch.cuda.device(z.device):
+        idx, dmin, stats = _search_into(z, weight, algo, True)
+    return idx, dmin, stats
+
+
+@search.register_fake
+def _(z, weight, algo=0):
+    shape = (z.shape[0],) + tuple(z.shape[2:])
+    return (z.new_empty(shape, dtype=torch.int64), z.new_empty(shape),
+            z.new_empty((4,), dtype=torch.int64))
+
+
+# ---------------------------------------------------------------------------
+# full forward (quantizer.py:63-101)
+# ---------------------------------------------------------------------------
+@torch.library.custom_op("vqb200::quantize", mutates_args=())
+def quantize(z: Tensor, weight: Tensor, beta: float, algo: int = 0
+             ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """(z_q, vq_loss, mse, indices, stats).  z_q is the straight-through VALUE
+    z + (e - z); vq_loss = mse + beta*mse; mse is the value of both
+    codebook_loss and commitment_loss."""
+    _need_cuda_f32(z, "z")
+    _need_cuda_f32(weight, "weight")
+    z = z.contiguous()
+    weight = weight.contiguous()
+    B, D, HW, K = _shape_bdhw(z, weight)
+    with torch.cuda.device(z.device):
+        idx, _, stats = _search_into(z, weight, algo, False)
+        z_q = torch.empty_like(z)
+        loss = torch.empty(2, dtype=torch.float32, device=z.device)
+        pbytes = lib().vqb_tail_partials_bytes(B * HW)
+        partials = _bytes(pbytes, z.device)
+        check(lib().vqb_gather_loss_st_f32(_p(z), _p(weight), _p(idx), B, D, HW, K, float(beta),
+                                           _p(z_q), _p(loss), _p(partials), pbytes, None, _stream()),
+              "vqb_gather_loss_st_f32")
+    return z_q, loss[1].clone(), loss[0].clone(), idx, stats
+
+
+@quantize.register_fake
+def _(z, weight, beta, algo=0):
+    shape = (z.shape[0],) + tuple(z.shape[2:])
+    return (torch.empty_like(z), z.new_empty(()), z.new_empty(()),
+            z.new_empty(shape, dtype=torch.int64), z.new_empty((4,), dtype=torch.int64))
+
+
+@torch.library.custom_op("vqb200::quantize_backward", mutates_args=())
+def quantize_backward(z: Tensor, weight: Tensor, indices: Tensor, g_zq: Optional[Tensor],
+                      g_vq: Optional[Tensor], beta: float, need_dE: bool) -> Tuple[Tensor, Tensor]:
+    """(dz, dE): dz = g_zq + g_vq*(2/n)(z-e); dE = g_vq*beta*(2/n) * index_add(e - z)."""
+    _need_cuda_f32(z, "z")
+    z = z.contiguous()
+    weight = weight.contiguous()
+    B, D, HW, K = _shape_bdhw(z, weight)
+    if g_zq is not None:
+        g_zq = g_zq.contiguous().to(torch.float32)
+    if g_vq is not None:
+        g_vq = g_vq.reshape(1).to(torch.float32).contiguous()
+    with torch.cuda.device(z.device):
+        dz = torch.empty_like(z)
+        dE = torch.zeros_like(weight) if need_dE else None
+        check(lib().vqb_backward_f32(_p(z), _p(weight), _p(indices), _p(g_zq), _p(g_vq), float(beta),
+                                     B, D, HW, K, _p(dz), _p(dE), None, _stream()),
+              "vqb_backward_f32")
+    if dE is None:
+        dE = weight.new_empty((0,))
+    return dz, dE
+
+
+@quantize_backward.register_fake
+def _(z, weight, indices, g_zq, g_vq, beta, need_dE):
+    return torch.empty_like(z), (torch.empty_like(weight) if need_dE else weight.new_empty((0,)))
+
+
+def _quantize_setup(ctx, inputs, output):
+    z, weight, beta, _algo = inputs
+    ctx.save_for_backward(z, weight, output[3])
+    ctx.beta = beta
+
+
+def _quantize_bwd(ctx, g_zq, g_vq, g_mse, g_idx, g_stats):
+    z, weight, idx = ctx.saved_tensors
+    need_dz, need_dE = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    dz, dE = quantize_backward(z, weight, idx, g_zq, g_vq, ctx.beta, bool(need_dE))
+    return (dz if need_dz else None), (dE if need_dE else None), None, None
+
+
+torch.library.register_autograd("vqb200::quantize", _quantize_bwd, setup_context=_quantize_setup)
+
+
+# ---------------------------------------------------------------------------
+# helper methods (quantizer.py:112-149)
+# ---------------------------------------------------------------------------
+@torch.library.custom_op("vqb200::codebook_entry", mutates_args=())
+def codebook_entry(weight: Tensor, indices: Tensor) -> Tuple[Tensor, Tensor]:
+    """(out[B,D,*spatial], err int32[1]); err != 0 iff an index is out of range."""
+    _need_cuda_f32(weight, "weight")
+    if not indices.is_cuda or indices.dtype != torch.int64:
+        raise RuntimeError("indices must be a CUDA int64 tensor")
+    weight = weight.contiguous()
+    indices = indices.contiguous()
+    K, D = int(weight.shape[0]), int(weight.shape[1])
+    B = int(indices.shape[0]) if indices.dim() > 0 else 1
+    HW = indices.numel() // max(B, 1) if B > 0 else 0
+    out = torch.empty((B, D) + tuple(indices.shape[1:]), dtype=torch.float32, device=weight.device)
+    err = torch.zeros(1, dtype=torch.int32, device=weight.device)
+    with torch.cuda.device(weight.device):
+        check(lib().vqb_gather_f32(_p(weight), _p(indices), B, D, HW, K, _p(out), _p(err), _stream()),
+              "vqb_gather_f32")
+    return out, err
+
+
+@codebook_entry.register_fake
+def _(weight, indices):
+    return (weight.new_empty((indices.shape[0], weight.shape[1]) + tuple(indices.shape[1:])),
+            weight.new_empty((1,), dtype=torch.int32))
+
+
+@torch.library.custom_op("vqb200::codebook_usage", mutates_args=())
+def codebook_usage(indices: Tensor, num_embeddings: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """(usage int64[K], used int64[1], err int32[1])."""
+    if not indices.is_cuda or indices.dtype != torch.int64:
+        raise RuntimeError("indices must be a CUDA int64 tensor")
+    indices = indices.contiguous()
+    hist = torch.empty(num_embeddings, dtype=torch.int64, device=indices.device)
+    used = torch.empty(1, dtype=torch.int64, device=indices.device)
+    err = torch.zeros(1, dtype=torch.int32, device=indices.device)
+    with torch.cuda.device(indices.device):
+        check(lib().vqb_hist_i64(_p(indices), indices.numel(), num_embeddings, _p(hist), _p(used),
+                                 _p(err), _stream()), "vqb_hist_i64")
+    return hist, used, err
+
+
+@codebook_usage.register_fake
+def _(indices, num_embeddings):
+    return (indices.new_empty((num_embeddings,)), indices.new_empty((1,)),
+            indices.new_empty((1,), dtype=torch.int32))
+
+
+# ---------------------------------------------------------------------------
+# extensions
+# ---------------------------------------------------------------------------
+@torch.library.custom_op("vqb200::code_sums", mutates_args=())
+def code_sums(z: Tensor, indices: Tensor, num_embeddings: int) -> Tuple[Tensor, Tensor]:
+    """(counts f32[K], sums f32[K,D]) = per-code token count and token sum."""
+    _need_cuda_f32(z, "z")
+    z = z.contiguous()
+    indices = indices.contiguous()
+    B, D = int(z.shape[0]), int(z.shape[1])
+    HW = z.numel() // max(B * D, 1)
+    counts = torch.zeros(num_embeddings, dtype=torch.float32, device=z.device)
+    sums = torch.zeros(num_embeddings, D, dtype=torch.float32, device=z.device)
+    with torch.cuda.device(z.device):
+        check(lib().vqb_code_sums_f32(_p(z), _p(indices), B, D, HW, num_embeddings, _p(counts),
+                                      _p(sums), _stream()), "vqb_code_sums_f32")
+    return counts, sums
+
+
+@code_sums.register_fake
+def _(z, indices, num_embeddings):
+    return z.new_empty((num_embeddings,)), z.new_empty((num_embeddings, z.shape[1]))
+
+
+@torch.library.custom_op("vqb200::ema_update",
+                         mutates_args=("weight", "cluster_size", "embed_sum"))
+def ema_update(weight: Tensor, cluster_size: Tensor, embed_sum: Tensor, counts: Tensor,
+               sums: Tensor, decay: float, eps: float) -> None:
+    for t, n in ((weight, "weight"), (cluster_size, "cluster_size"), (embed_sum, "embed_sum"),
+                 (counts, "counts"), (sums, "sums")):
+        _need_cuda_f32(t, n)
+        if not t.is_contiguous():
+            raise RuntimeError(f"{n} must be contiguous")
+    K, D = int(weight.shape[0]), int(weight.shape[1])
+    scratch = torch.empty(1, dtype=torch.float32, device=weight.device)
+    with torch.cuda.device(weight.device):
+        check(lib().vqb_ema_update_f32(_p(weight), _p(cluster_size), _p(embed_sum), _p(counts),
+                                       _p(sums), K, D, float(decay), float(eps), _p(scratch),
+                                       _stream()), "vqb_ema_update_f32")
+
+
+@torch.library.custom_op("vqb200::pack_argmin_keys", mutates_args=())
+def pack_argmin_keys(dmin: Tensor, indices: Tensor, index_offset: int) -> Tensor:
+    _need_cuda_f32(dmin, "dmin")
+    dmin = dmin.contiguous()
+    indices = indices.contiguous()
+    keys = torch.empty(indices.shape, dtype=torch.int64, device=dmin.device)
+    with torch.cuda.device(dmin.device):
+        check(lib().vqb_pack_argmin_keys(_p(dmin), _p(indices), indices.numel(), int(index_offset),
+                                         _p(keys), _stream()), "vqb_pack_argmin_keys")
+    return keys
+
+
+@pack_argmin_keys.register_fake
+def _(dmin, indices, index_offset):
+    return torch.empty_like(indices)
+
+
+@torch.library.custom_op("vqb200::unpack_argmin_keys", mutates_args=())
+def unpack_argmin_keys(keys: Tensor) -> Tuple[Tensor, Tensor]:
+    if not keys.is_cuda or keys.dtype != torch.int64:
+        raise RuntimeError("keys must be a CUDA int64 tensor")
+    keys = keys.contiguous()
+    idx = torch.empty_like(keys)
+    dmin = torch.empty(keys.shape, dtype=torch.float32, device=keys.device)
+    with torch.cuda.device(keys.device):
+        check(lib().vqb_unpack_argmin_keys(_p(keys), keys.numel(), _p(idx), _p(dmin), _stream()),
+              "vqb_unpack_argmin_keys")
+    return idx, dmin
+
+
+@unpack_argmin_keys.register_fake
+def _(keys):
+    return torch.empty_like(keys), keys.new_empty(keys.shape, dtype=torch.float32)
+
+
+def fma_peak_tflops(packed: bool, iters: int = 4096, repeats: int = 5) -> float:
+    """Measured FP32 FMA peak of the current device (roofline denominator for the
+    low-D search): best of `repeats`, CUDA events on the current stream."""
+    sink = torch.zeros(1, dtype=torch.float32, device="cuda")
+    flops = ctypes.c_double(0.0)
+    best = 0.0
+    for _ in range(repeats + 1):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(lib().vqb_fma_peak_launch(int(packed), iters, _p(sink), ctypes.byref(flops), _stream()),
+              "vqb_fma_peak_launch")
+        b.record()
+        b.synchronize()
+        ms = a.elapsed_time(b)
+        best = max(best, flops.value / (ms * 1e-3) / 1e12)
+    return best

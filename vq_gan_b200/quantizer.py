@@ -1,0 +1,110 @@
+"""Drop-in `VectorQuantizer` running on libvqb200 (sm_100a).
+
+Mirrors the reference class in vqgan_ldm_baseline/models/quantizer.py:17-149:
+same constructor, attributes, `forward` outputs `(z_q, loss_dict, indices)`,
+`get_codebook_entry`, `get_codebook_usage`, and a `state_dict()` holding exactly
+`embedding.weight`.  Inputs must be CUDA float32 tensors; there is no CPU path.
+"""
+from typing import Dict, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._cabi import ALGO_AUTO, ALGO_NAMES
+
+
+class VectorQuantizer(nn.Module):
+    """Nearest-codebook bottleneck (reference: quantizer.py:17-149).
+
+    Args (quantizer.py:33-38):
+        num_embeddings: codebook size K
+        embedding_dim: code dimension D
+        commitment_cost: beta, weight of the commitment term
+    Keyword-only extensions (defaults reproduce the reference exactly):
+        return_format: "reference" -> (z_q, loss_dict, indices) as quantizer.py:110;
+            "taming" -> (z_q, vq_loss, (perplexity, None, indices)) -- values parity-unpinned
+        lazy_stats: keep the two logged losses as 0-dim device tensors instead of
+            Python floats (skips the host sync of quantizer.py:106-107)
+        algo: search kernel override (0 auto, 1 low-D FMA, 2 fp32 tile, 3 tcgen05)
+    """
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, commitment_cost: float = 0.25, *,
+                 return_format: str = "reference", lazy_stats: bool = False, algo: int = ALGO_AUTO):
+        super().__init__()
+        if return_format not in ("reference", "taming"):
+            raise ValueError(f"unknown return_format {return_format!r}")
+        if algo not in ALGO_NAMES:
+            raise ValueError(f"unknown algo {algo}")
+        self.num_embeddings = num_embeddings
+        self.embedding_dim = embedding_dim
+        self.commitment_cost = commitment_cost
+        self.return_format = return_format
+        self.lazy_stats = lazy_stats
+        self.algo = algo
+        # same two RNG draws, in the same order, as quantizer.py:47-48, so that
+        # torch.manual_seed(42) (train_vqgan.py:117) yields the same codebook
+        self.embedding = nn.Embedding(num_embeddings, embedding_dim)
+        self.embedding.weight.data.uniform_(-1.0 / num_embeddings, 1.0 / num_embeddings)
+        self.last_search_stats = None  # int64[4] device tensor of the last forward
+
+    # -- forward (quantizer.py:50-110) ---------------------------------------
+    def forward(self, z: torch.Tensor):
+        if z.dim() != 4:
+            raise RuntimeError(f"expected z of shape [B, C, H, W], got {tuple(z.shape)}")
+        if z.shape[1] != self.embedding_dim:
+            raise RuntimeError(
+                f"z has {z.shape[1]} channels but embedding_dim is {self.embedding_dim}")
+        if z.dtype != torch.float32:
+            z = z.float()
+        z_q, vq_loss, mse, indices, stats = ops.quantize(z, self.embedding.weight,
+                                                         float(self.commitment_cost), self.algo)
+        self.last_search_stats = stats
+        if self.return_format == "taming":
+            usage, _, _ = ops.codebook_usage(indices, self.num_embeddings)
+            p = usage.double() / max(indices.numel(), 1)
+            perplexity = torch.exp(-(p * torch.log(p + 1e-10)).sum()).float()
+            return z_q, vq_loss, (perplexity, None, indices)
+        if self.lazy_stats:
+            m = mse.detach()
+            loss_dict = {"vq_loss": vq_loss, "codebook_loss": m, "commitment_loss": m}
+        else:
+            m = mse.item()  # ONE device->host sync for both logged values
+            loss_dict = {"vq_loss": vq_loss, "codebook_loss": m, "commitment_loss": m}
+        return z_q, loss_dict, indices
+
+    # -- quantizer.py:112-132 --------------------------------------------------
+    def get_codebook_entry(self, indices: torch.Tensor, strict: bool = True) -> torch.Tensor:
+        if indices.dim() != 3:
+            raise RuntimeError(f"expected indices of shape [B, H, W], got {tuple(indices.shape)}")
+        out, err = ops.codebook_entry(self.embedding.weight.detach(), indices.long())
+        if strict and int(err.item()) != 0:
+            raise IndexError("index out of range in get_codebook_entry")
+        return out
+
+    # -- quantizer.py:134-149 --------------------------------------------------
+    def get_codebook_usage(self, indices: torch.Tensor) -> Tuple[torch.Tensor, float]:
+        usage, used, err = ops.codebook_usage(indices.long(), self.num_embeddings)
+        host = torch.stack([used[0], err[0].long()]).cpu()  # one sync
+        if int(host[1]) != 0:
+            raise RuntimeError("get_codebook_usage: index outside [0, num_embeddings)")
+        # the reference computes float32 mean of (usage > 0): count / K rounded to fp32
+        ratio = (torch.tensor(float(host[0]), dtype=torch.float32) / self.num_embeddings).item()
+        return usage, ratio
+
+    # -- bulk encode (VQVAE.encode_to_indices, vq_vae.py:162-175) -------------
+    @torch.no_grad()
+    def encode_indices(self, z: torch.Tensor) -> torch.Tensor:
+        """Search only: indices [B, H, W] without z_q / loss."""
+        idx, _, stats = ops.search(z.float(), self.embedding.weight.detach(), self.algo)
+        self.last_search_stats = stats
+        return idx
+
+    def extra_repr(self) -> str:
+        return (f"num_embeddings={self.num_embeddings}, embedding_dim={self.embedding_dim}, "
+                f"commitment_cost={self.commitment_cost}, algo={ALGO_NAMES[self.algo]}")
+
+
+def usage_ratio_like_reference(usage: torch.Tensor) -> float:
+    """(usage > 0).float().mean().item() -- quantizer.py:147, for host-side checks."""
+    return (usage > 0).float().mean().item()
