@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the VQ bottleneck hot path (BASELINE.json metric: VQ lookup tokens/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1]
+    python bench.py --impl reference ...      # the reference op sequence on the host CPU
+
+A step = one quantizer forward + backward over one batch of synthetic latents
+(per GPU: 1M tokens for c2/c3).  Weak scaling: every rank has its own batch, the
+codebook is replicated, and the per-step codebook statistics (dE, histogram,
+squared error) are all-reduced over NCCL.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (images per GPU, D, H, W, K, description)
+    "c2": (1024, 4, 32, 32, 16384, "low-dim f=4 LDM latent: 1M tokens x d=4 x codebook 16384, fwd+bwd"),
+    "c3": (1024, 256, 32, 32, 16384, "high-dim tokenizer: 1M tokens x d=256 x codebook 16384, fwd+bwd"),
+    "c1": (4, 256, 32, 32, 128, "train_vqgan.py default: 4096 tokens x d=256 x codebook 128, fwd+bwd"),
+}
+CPU_CHUNK_TOKENS = {"c2": 32768, "c3": 16384, "c1": 4096}
+BETA = 0.25
+N_ROTATE = 8  # distinct input sets cycled through so the working set exceeds the 126 MB L2
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p.get("hbm_gbs"), "bf16_tflops": p.get("bf16_tflops"),
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ---------------------------------------------------------------------------
+# clocks (pynvml sampling thread during the timed region)
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+
+    def __init__(self, index, period=0.02):
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                    "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the reference op sequence (oracle port) on the host cores
+# ---------------------------------------------------------------------------
+def cpu_step_fn(workload):
+    """Returns (fn, tokens_per_call): one fwd+bwd of the reference op sequence on a
+    bounded token chunk of the workload (the reference cannot hold [1M, 16384])."""
+    from oracle import vq_oracle as orc
+    _, D, H, W, K, _ = WORKLOADS[workload]
+    chunk = CPU_CHUNK_TOKENS[workload]
+    B = max(chunk // (H * W), 1)
+    z = torch.randn(B, D, H, W, generator=torch.Generator().manual_seed(0))
+    E = torch.randn(K, D, generator=torch.Generator().manual_seed(1))
+    g = torch.randn(B, D, H, W, generator=torch.Generator().manual_seed(2))
+
+    def fn():
+        return orc.autograd_step(z, E, BETA, g)
+    return fn, B * H * W
+
+
+def run_cpu_baseline(workload, budget_s=12.0, max_calls=6):
+    torch.set_num_threads(os.cpu_count() or 1)
+    fn, tokens = cpu_step_fn(workload)
+    fn()  # warm-up
+    times = []
+    t_all = time.perf_counter()
+    while len(times) < max_calls and (time.perf_counter() - t_all) < budget_s:
+        t0 = time.perf_counter()
+        fn()
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return {"value": tokens / best, "unit": "tokens/s", "cores": torch.get_num_threads(),
+            "kind": "port",
+            "sample": f"{tokens}-token chunk of {workload} (fwd+bwd, reference op sequence in torch CPU "
+                      f"fp32, best of {len(times)})"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    fn, tokens = cpu_step_fn(args.workload)
+    for _ in range(max(args.warmup, 1) if args.warmup else 0):
+        fn()
+    steps = max(args.steps, 1)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = time.perf_counter() - t0
+    value = tokens * steps / dt
+    desc = WORKLOADS[args.workload][5]
+    line = {
+        "impl": "reference", "metric": "vq_lookup_tokens_per_sec", "value": value, "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "tokens_per_step": tokens,
+                   "note": "reference op sequence (quantizer.py:63-98 + autograd) on host CPU; each step is a "
+                           "bounded token chunk because the reference materialises [N, K]"},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": torch.get_num_threads(),
+                         "kind": "port", "sample": f"{tokens}-token chunk x {steps} steps"},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def gpu_strawman_tokens_per_s(workload, device):
+    """The reference op sequence with stock torch CUDA ops, on one chunk (context only)."""
+    _, D, H, W, K, _ = WORKLOADS[workload]
+    chunk = CPU_CHUNK_TOKENS[workload]
+    B = max(chunk // (H * W), 1)
+    z = torch.randn(B, D, H, W, device=device, requires_grad=True)
+    E = torch.randn(K, D, device=device, requires_grad=True)
+    g = torch.randn(B, D, H, W, device=device)
+
+    def fn():
+        rows = z.permute(0, 2, 3, 1).reshape(-1, D)
+        d = (rows ** 2).sum(1, keepdim=True) + (E ** 2).sum(1) - 2 * rows @ E.t()
+        idx = torch.argmin(d, 1)
+        e = torch.nn.functional.embedding(idx, E).view(B, H, W, D).permute(0, 3, 1, 2).contiguous()
+        loss = torch.nn.functional.mse_loss(e.detach(), z) + BETA * torch.nn.functional.mse_loss(e, z.detach())
+        zq = z + (e - z).detach()
+        (loss + (zq * g).sum()).backward()
+        z.grad = None
+        E.grad = None
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        fn()
+    b.record()
+    b.synchronize()
+    return B * H * W * 5 / (a.elapsed_time(b) * 1e-3)
+
+
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    from vq_gan_b200 import VectorQuantizer, ops
+    from vq_gan_b200 import distributed as vdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    B, D, H, W, K, desc = WORKLOADS[args.workload]
+    tokens = B * H * W
+    peaks = load_peaks()
+
+    vq = VectorQuantizer(K, D, BETA, lazy_stats=True).to(device)
+    with torch.no_grad():
+        vq.embedding.weight.copy_(torch.randn(K, D, generator=torch.Generator().manual_seed(1)))
+    weight = vq.embedding.weight
+
+    n_rot = N_ROTATE if args.workload == "c2" else (2 if args.workload == "c3" else 64)
+    gen = torch.Generator(device=device).manual_seed(100 + rank)
+    zs = [torch.randn(B, D, H, W, device=device, generator=gen).requires_grad_(True) for _ in range(n_rot)]
+    gs = [torch.randn(B, D, H, W, device=device, generator=gen) for _ in range(min(n_rot, 2))]
+    bytes_per_set = zs[0].numel() * 4 * 4 + tokens * 8  # z, g, z_q, dz + idx
+
+    def step(i):
+        z = zs[i % n_rot]
+        z.grad = None
+        weight.grad = None
+        z_q, loss_dict, idx = vq(z)
+        (loss_dict["vq_loss"] + (z_q * gs[i % len(gs)]).sum()).backward()
+        if world > 1:
+            # data parallel: one packed all-reduce of dE + histogram + squared-error sum
+            usage, _, _ = ops.codebook_usage(idx, K)
+            sq = (loss_dict["codebook_loss"] * float(z.numel())).reshape(1)
+            dE, hist, s = vdist.allreduce_stats(weight.grad, usage, sq, average_dE=True)
+            weight.grad.copy_(dE)
+        z.grad = None  # hand dz back to the caching allocator: no cudaMalloc in the timed region
+        return loss_dict["vq_loss"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    # FMA peak of this device (roofline denominator for the CUDA-core search)
+    fma_scalar = ops.fma_peak_tflops(False)
+    fma_packed = ops.fma_peak_tflops(True)
+    fma_peak = max(fma_scalar, fma_packed)
+
+    warmup = max(args.warmup, 3)
+    for i in range(warmup):
+        step(i)
+    barrier()
+
+    # ---- device-resident timing: exactly K steps between two events --------
+    ops.PROFILE = []
+    launches0 = ops.LAUNCHES["total"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            step(i)
+        ev1.record()
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    gpu_launches = ops.LAUNCHES["total"] - launches0
+    search_ms = [a.elapsed_time(b) for a, b in ops.PROFILE]
+    ops.PROFILE = None
+    if world > 1:
+        t = torch.tensor([ms_total], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    stats = vq.last_search_stats.tolist()
+
+    # ---- end to end through the public module API with host buffers --------
+    z_host = [torch.randn(B, D, H, W, generator=torch.Generator().manual_seed(200 + rank + j)).pin_memory()
+              for j in range(2)]
+    idx_host = torch.empty(B, H, W, dtype=torch.int64).pin_memory()
+    vq_sync = VectorQuantizer(K, D, BETA).to(device)
+    vq_sync.embedding.weight = weight
+
+    def e2e_step(i):
+        z = z_host[i % 2].to(device, non_blocking=True).requires_grad_(True)
+        weight.grad = None
+        z_q, loss_dict, idx = vq_sync(z)  # reference contract: Python floats in loss_dict (host sync)
+        (loss_dict["vq_loss"] + (z_q * gs[i % len(gs)]).sum()).backward()
+        if world > 1:
+            usage, _, _ = ops.codebook_usage(idx, K)
+            sq = torch.tensor([loss_dict["codebook_loss"] * z.numel()], device=device)
+            dE, hist, s = vdist.allreduce_stats(weight.grad, usage, sq, average_dE=True)
+            weight.grad.copy_(dE)
+        idx_host.copy_(idx, non_blocking=True)
+        return loss_dict["vq_loss"].item()
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+
+    if rank == 0:
+        algo = int(stats[1])
+        flops = 2.0 * tokens * K * D
+        s_ms = statistics.mean(search_ms) if search_ms else float("nan")
+        if algo == 3:
+            bound, peak, unit = "tensor", peaks["bf16_tflops_sustained"], "TFLOP/s"
+            peak_note = f"cuBLAS bf16 sustained, {peaks['source']} (algorithmic flops; x3 executed for bf16x3)"
+        else:
+            bound, peak, unit = "fma", fma_peak, "TFLOP/s"
+            peak_note = ("FP32 FMA peak measured in this run by vqb_fma_peak_launch "
+                         f"(scalar FFMA {fma_scalar:.1f}, packed FFMA2 {fma_packed:.1f} TFLOP/s); "
+                         "MEASURED_PEAKS.json has no FMA figure")
+        achieved = flops / (s_ms * 1e-3) / 1e12
+        roofline = {"bound": bound, "kernel": {1: "search_lowd_kernel", 2: "search_fp32_kernel",
+                                               3: "search_tc_kernel"}.get(algo, str(algo)),
+                    "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                    "traffic": None, "kernel_ms": s_ms, "algorithmic_flops_per_launch": flops,
+                    "peak_source": peak_note,
+                    "step_share": s_ms * len(search_ms) / ms_total if search_ms else None}
+        # HBM-side kernels (tail + backward): algorithmic bytes per token 8D+8 and 12D+8
+        line = {
+            "metric": "vq_lookup_tokens_per_sec", "value": tokens * world * args.steps / (ms_total * 1e-3),
+            "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "tokens_per_gpu_per_step": tokens,
+                       "D": D, "K": K, "beta": BETA, "parallelism": f"dp{world}",
+                       "l2": f"{n_rot} rotating input sets ({n_rot * bytes_per_set / 1e6:.0f} MB) > 126 MB L2",
+                       "search_algo": {1: "lowd_fma", 2: "fp32_tile", 3: "tcgen05_bf16x3"}.get(algo, str(algo)),
+                       "rescored_tokens_last_step": int(stats[0])},
+            "roofline": roofline,
+            "e2e": {"value": tokens * world * e2e_steps / (e2e_ms * 1e-3), "unit": "tokens/s",
+                    "h2d_bytes_per_step": zs[0].numel() * 4, "d2h_bytes_per_step": tokens * 8 + 8,
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                    "api": "VectorQuantizer.forward + backward on pinned host latents, indices and loss read back"},
+            "gpu_launches": gpu_launches,
+            "clocks": clk.summary(),
+            "fma_peak_tflops": {"scalar": fma_scalar, "packed": fma_packed},
+        }
+        if world == 1:
+            line["cpu_baseline"] = run_cpu_baseline(args.workload)
+            if not args.no_strawman:
+                try:
+                    line["gpu_strawman_tokens_per_s"] = gpu_strawman_tokens_per_s(args.workload, device)
+                except Exception as e:  # context only, never fatal
+                    line["gpu_strawman_tokens_per_s"] = f"failed: {type(e).__name__}"
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-strawman", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run --nproc-per-node N")
+    run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

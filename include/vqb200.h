@@ -41,7 +41,7 @@ extern "C" {
 #define VQB_ALGO_AUTO 0
 #define VQB_ALGO_LOWD_FMA 1   /* D <= 16: packed-FFMA2 CUDA-core kernel         */
 #define VQB_ALGO_FP32_TILE 2  /* any D: fp32 register-tiled CUDA-core kernel    */
-#define VQB_ALGO_TCGEN05 3    /* D % 64 == 0, 64 <= D <= 512: bf16x3 tcgen05/TMEM */
+#define VQB_ALGO_TCGEN05 3    /* D in {64,128,192,256}: bf16x3 tcgen05/TMEM     */
 
 typedef void* vqb_stream_t; /* a cudaStream_t */
 
@@ -57,6 +57,9 @@ VQB_API const char* vqb_last_error(void);
 /* sm count, compute capability and opt-in shared memory of `device` */
 VQB_API int vqb_device_query(int device, int* sm_count, int* cc_major, int* cc_minor,
                      size_t* smem_optin_bytes);
+
+/* launch-shape tuning knobs for experiments ("lowd_variant" = 0..4); defaults are the shipped ones */
+VQB_API int vqb_tune(const char* key, int value);
 
 /* ---- codebook pre-pass -------------------------------------------------
  * Replaces `torch.sum(self.embedding.weight ** 2, dim=1)` (quantizer.py:70) and

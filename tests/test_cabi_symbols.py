@@ -44,7 +44,8 @@ def test_version_and_size_queries_without_gpu():
     assert 0 < small < big
     assert lib.vqb_codebook_pack_bytes(0, 4) == 0
     assert lib.vqb_tail_partials_bytes(1 << 20) >= 8 * (1 << 15)
-    assert lib.vqb_search_workspace_bytes(4, 32, 64, 128, 0) == 0
+    assert lib.vqb_search_workspace_bytes(4, 4, 64, 128, 0) == 0
+    assert lib.vqb_search_workspace_bytes(4, 32, 64, 128, 0) >= 8 * 256
 
 
 def test_missing_library_fails_loudly(monkeypatch):

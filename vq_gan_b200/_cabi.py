@@ -21,6 +21,7 @@ PROTOTYPES = {
     "vqb_last_error": (c_char_p, []),
     "vqb_device_query": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                  POINTER(c_size_t)]),
+    "vqb_tune": (c_int, [c_char_p, c_int]),
     "vqb_codebook_pack_bytes": (c_size_t, [c_int, c_int]),
     "vqb_codebook_prepare_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "vqb_search_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64, c_int, c_int]),

@@ -62,6 +62,15 @@ extern "C" int vqb_device_query(int device, int* sm, int* cc_major, int* cc_mino
     return VQB_OK;
 }
 
+extern "C" int vqb_tune(const char* key, int value) {
+    if (key && strcmp(key, "lowd_variant") == 0 && value >= 0 && value <= 4) {
+        set_lowd_variant(value);
+        return VQB_OK;
+    }
+    set_error("vqb_tune: unknown key or value (%s = %d)", key ? key : "(null)", value);
+    return VQB_ERR_INVALID_ARG;
+}
+
 extern "C" size_t vqb_codebook_pack_bytes(int K, int D) {
     if (K <= 0 || D <= 0) return 0;
     return pack_layout(K, D).total;
@@ -96,6 +105,7 @@ extern "C" size_t vqb_search_workspace_bytes(int64_t B, int D, int64_t HW, int K
     if (B < 0 || HW < 0 || D <= 0 || K <= 0) return 0;
     const int a = resolve_algo(algo, D);
     if (a == VQB_ALGO_TCGEN05) return search_tc_workspace_bytes(B * HW, D, K);
+    if (a == VQB_ALGO_FP32_TILE) return search_fp32_workspace_bytes(B * HW);
     return 0;
 }
 
@@ -135,7 +145,8 @@ extern "C" int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, cons
             rc = launch_search_lowd(z, B, D, HW, K, pack, idx_out, dmin_out, s);
             break;
         case VQB_ALGO_FP32_TILE:
-            rc = launch_search_fp32(z, B, D, HW, E, K, pack, nullptr, nullptr, 0, idx_out, dmin_out, s);
+            rc = launch_search_fp32(z, B, D, HW, E, K, pack, nullptr, nullptr, 0, workspace, workspace_bytes,
+                                    idx_out, dmin_out, s);
             break;
         case VQB_ALGO_TCGEN05:
             if (!tc_eligible_dim(D)) {

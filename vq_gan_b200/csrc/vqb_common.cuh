@@ -31,7 +31,7 @@ int cuda_fail(cudaError_t e, const char* what);
 int sm_count();  // cached per current device
 
 // ---- packed codebook layout ----------------------------------------------
-// header (int32[64]): [0] first NaN code (K if none) [1] K [2] D
+// header (int32[64]): [0] first NaN code (K if none) [1] K [2] D [4] float bits of max 0.5|e|^2
 // half_norm: float[Kpad]  0.5|e_k|^2, +inf for k >= K.  Read as consecutive
 //            (h[2p], h[2p+1]) pairs by the low-D kernel.
 // pairs    : float[Kpad/2][2D]  (D <= 16)  e_d(2p), e_d(2p+1) interleaved per d
@@ -40,7 +40,7 @@ constexpr int kPadCodes = 256;
 constexpr int kHeaderBytes = 256;
 constexpr int kLowDMax = 16;
 constexpr int kTcMinD = 64;
-constexpr int kTcMaxD = 512;
+constexpr int kTcMaxD = 256;
 
 __host__ __device__ inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
 __host__ __device__ inline size_t round_up_z(size_t x, size_t m) { return (x + m - 1) / m * m; }
@@ -108,13 +108,15 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 int launch_codebook_prepare(const float* E, int K, int D, void* pack, cudaStream_t s);
 int launch_search_lowd(const float* z, int64_t B, int D, int64_t HW, int K, const void* pack,
                        int64_t* idx_out, float* dmin_out, cudaStream_t s);
+size_t search_fp32_workspace_bytes(int64_t n_rows);
 int launch_search_fp32(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                        const void* pack, const int32_t* token_list, const int32_t* list_count,
-                       int64_t max_list, int64_t* idx_out, float* dmin_out, cudaStream_t s);
+                       int64_t max_list, void* keys_ws, size_t keys_bytes, int64_t* idx_out,
+                       float* dmin_out, cudaStream_t s);
 size_t search_tc_workspace_bytes(int64_t n_tokens, int D, int K);
 int launch_search_tc(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                      const void* pack, int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes,
                      int64_t* stats_out, cudaStream_t s);
-int launch_nan_override(const void* pack, int K, int64_t n_tokens, int64_t* idx_out, cudaStream_t s);
+void set_lowd_variant(int v);
 
 }  // namespace vqb

@@ -11,6 +11,7 @@ __global__ void prepare_header_kernel(int* header, int K, int D) {
         header[0] = K;  // first NaN code (atomicMin below)
         header[1] = K;
         header[2] = D;
+        header[4] = 0;  // bits of max_k 0.5|e_k|^2 (atomicMax below; non-negative floats order as ints)
     }
 }
 
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(256) codebook_prepare_kernel(const float* __re
     if (lane == 0) {
         half_norm[k] = live ? 0.5f * sq : INFINITY;
         if (live && (bad || sq != sq)) atomicMin(&header[0], k);
+        if (live && sq == sq) atomicMax(&header[4], __float_as_int(0.5f * sq));
     }
 }
 

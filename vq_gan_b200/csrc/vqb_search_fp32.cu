@@ -1,12 +1,17 @@
 // Nearest-code search for any embedding dimension on the CUDA cores (fp32).
 // Replaces quantizer.py:68-76 of the reference for 16 < D < 64 or D not a
 // multiple of 64, and is the exact fp32 re-score of the near-ties flagged by the
-// bf16x3 tensor kernel (then it runs on a compacted token list).
+// bf16x3 tensor kernel (then it runs on a compacted token list whose length is
+// only known on the device).
 //
-// Register-tiled 128 tokens x 128 codes per CTA, 8x8 scores per thread, the
-// score tile never leaves registers: epilogue d = 0.5|e|^2 - z.e feeds a
-// per-thread running (min, index), reduced over the 16 threads that share a
-// token row once all code tiles are done.  Lowest index wins ties.
+// Work item = (128-token tile, code split).  Register-tiled 128 tokens x 128
+// codes, 8x8 scores per thread, the score tile never leaves registers: epilogue
+// d = 0.5|e|^2 - z.e (z.e accumulated with one fmaf per dimension, d ascending)
+// feeds a per-thread running (min, index), reduced over the 16 threads that
+// share a token row.  With more than one code split the partial winners meet in
+// a 64-bit atomicMin on (ordered score bits, index) keys -- lowest index wins
+// ties -- and a finalize pass unpacks them.  CTAs are persistent and stride over
+// the work items so a device-side token count needs no host sync.
 #include "vqb_common.cuh"
 
 namespace vqb {
@@ -17,11 +22,25 @@ constexpr int kFtDk = 16;
 constexpr int kFtThreads = 256;
 constexpr int kFtPad = 4;
 
+__device__ __forceinline__ unsigned long long score_key(float d, int idx) {
+    int bits = __float_as_int(d);
+    if (bits < 0) bits ^= 0x7fffffff;                 // monotone signed order
+    const unsigned int u = (unsigned int)bits ^ 0x80000000u;  // -> monotone unsigned order
+    return ((unsigned long long)u << 32) | (unsigned int)idx;
+}
+__device__ __forceinline__ void key_unpack(unsigned long long key, float& d, int& idx) {
+    idx = (int)(unsigned int)(key & 0xffffffffull);
+    int bits = (int)((unsigned int)(key >> 32) ^ 0x80000000u);
+    if (bits < 0) bits ^= 0x7fffffff;
+    d = __int_as_float(bits);
+}
+
 __global__ void __launch_bounds__(kFtThreads, 2)
     search_fp32_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW,
                        const float* __restrict__ E, int K, const unsigned char* __restrict__ pack,
                        PackLayout L, const int32_t* __restrict__ token_list,
-                       const int32_t* __restrict__ list_count, int64_t* __restrict__ idx_out,
+                       const int32_t* __restrict__ list_count, int splits, int codes_per_split,
+                       unsigned long long* __restrict__ keys, int64_t* __restrict__ idx_out,
                        float* __restrict__ dmin_out) {
     __shared__ __align__(16) float As[kFtDk][kFtTokens + kFtPad];
     __shared__ __align__(16) float Bs[kFtDk][kFtCodes + kFtPad];
@@ -31,134 +50,200 @@ __global__ void __launch_bounds__(kFtThreads, 2)
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int64_t count = token_list ? (int64_t)(*list_count) : N;
-    const int64_t m0 = (int64_t)blockIdx.x * kFtTokens;
-    if (m0 >= count) return;
+    const int64_t n_tiles = (count + kFtTokens - 1) / kFtTokens;
+    const int64_t n_items = n_tiles * splits;
     const float* half_norm = reinterpret_cast<const float*>(pack + L.off_half_norm);
     const int first_nan = reinterpret_cast<const int*>(pack)[0];
 
-    if (tid < kFtTokens) {
-        const int64_t r = m0 + tid;
-        int64_t t = -1;
-        if (r < count) t = token_list ? (int64_t)token_list[r] : r;
-        tok_id[tid] = t;
-        if (t >= 0) {
-            const int64_t b = t / HW;
-            tok_off[tid] = (b * D) * HW + (t - b * HW);
-        } else {
-            tok_off[tid] = -1;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int64_t tile = item / splits;
+        const int split = (int)(item - tile * splits);
+        const int64_t m0 = tile * kFtTokens;
+        const int n_begin = split * codes_per_split;
+        int n_end = n_begin + codes_per_split;
+        if (n_end > K) n_end = K;
+
+        __syncthreads();  // previous item is done with tok_off / tok_id
+        if (tid < kFtTokens) {
+            const int64_t r = m0 + tid;
+            int64_t t = -1;
+            if (r < count) t = token_list ? (int64_t)token_list[r] : r;
+            tok_id[tid] = t;
+            if (t >= 0) {
+                const int64_t b = t / HW;
+                tok_off[tid] = (b * D) * HW + (t - b * HW);
+            } else {
+                tok_off[tid] = -1;
+            }
         }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    float best[8];
-    int bidx[8];
+        float best[8];
+        int bidx[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        best[i] = INFINITY;
-        bidx[i] = 0;
-    }
-
-    for (int n0 = 0; n0 < K; n0 += kFtCodes) {
-        float acc[8][8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-
-        for (int k0 = 0; k0 < D; k0 += kFtDk) {
-#pragma unroll
-            for (int i = 0; i < (kFtDk * kFtTokens) / kFtThreads; ++i) {
-                const int e = tid + i * kFtThreads;
-                const int kk = e / kFtTokens, mm = e % kFtTokens;
-                const int64_t off = tok_off[mm];
-                float v = 0.f;
-                if (off >= 0 && k0 + kk < D) v = __ldg(z + off + (int64_t)(k0 + kk) * HW);
-                As[kk][mm] = v;
-            }
-#pragma unroll
-            for (int i = 0; i < (kFtDk * kFtCodes) / kFtThreads; ++i) {
-                const int e = tid + i * kFtThreads;
-                const int nn = e / kFtDk, kk = e % kFtDk;
-                float v = 0.f;
-                if (n0 + nn < K && k0 + kk < D) v = __ldg(E + (size_t)(n0 + nn) * D + k0 + kk);
-                Bs[kk][nn] = v;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int kk = 0; kk < kFtDk; ++kk) {
-                const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-                const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
-                const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-                const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
-                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-            }
-            __syncthreads();
+        for (int i = 0; i < 8; ++i) {
+            best[i] = INFINITY;
+            bidx[i] = 0;
         }
-        // epilogue: codes visited in increasing index order per thread
+
+        for (int n0 = n_begin; n0 < n_end; n0 += kFtCodes) {
+            float acc[8][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
-            const float h = half_norm[n];  // +inf beyond K (Kpad is a multiple of 256)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float d = h - acc[i][j];
-                if (d < best[i]) {
-                    best[i] = d;
-                    bidx[i] = n;
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+            for (int k0 = 0; k0 < D; k0 += kFtDk) {
+#pragma unroll
+                for (int i = 0; i < (kFtDk * kFtTokens) / kFtThreads; ++i) {
+                    const int e = tid + i * kFtThreads;
+                    const int kk = e / kFtTokens, mm = e % kFtTokens;
+                    const int64_t off = tok_off[mm];
+                    float v = 0.f;
+                    if (off >= 0 && k0 + kk < D) v = __ldg(z + off + (int64_t)(k0 + kk) * HW);
+                    As[kk][mm] = v;
+                }
+#pragma unroll
+                for (int i = 0; i < (kFtDk * kFtCodes) / kFtThreads; ++i) {
+                    const int e = tid + i * kFtThreads;
+                    const int nn = e / kFtDk, kk = e % kFtDk;
+                    float v = 0.f;
+                    if (n0 + nn < K && k0 + kk < D) v = __ldg(E + (size_t)(n0 + nn) * D + k0 + kk);
+                    Bs[kk][nn] = v;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int kk = 0; kk < kFtDk; ++kk) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+                    const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+                    const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+                    const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+                    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                }
+                __syncthreads();
+            }
+            // epilogue: codes visited in increasing index order per thread
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                const float h = half_norm[n];  // +inf beyond K (Kpad is a multiple of 256)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float d = h - acc[i][j];
+                    if (d < best[i]) {
+                        best[i] = d;
+                        bidx[i] = n;
+                    }
                 }
             }
         }
-    }
 
-    // reduce over the 16 threads (tx) sharing each token row
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best[i], o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bidx[i], o);
-            if (ov < best[i] || (ov == best[i] && oi < bidx[i])) {
-                best[i] = ov;
-                bidx[i] = oi;
-            }
-        }
-    }
-    if (tx == 0) {
+        // reduce over the 16 threads (tx) sharing each token row
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int row = i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4);
-            const int64_t t = tok_id[row];
-            if (t >= 0) {
-                int r = bidx[i];
-                if (first_nan < K) r = (best[i] == INFINITY) ? 0 : first_nan;
-                idx_out[t] = r;
-                if (dmin_out) dmin_out[t] = best[i];
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best[i], o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bidx[i], o);
+                if (ov < best[i] || (ov == best[i] && oi < bidx[i])) {
+                    best[i] = ov;
+                    bidx[i] = oi;
+                }
+            }
+        }
+        if (tx == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+                const int64_t t = tok_id[row];
+                if (t < 0) continue;
+                if (keys != nullptr) {
+                    atomicMin(keys + (m0 + row), score_key(best[i], bidx[i]));
+                } else {
+                    int r = bidx[i];
+                    if (first_nan < K) r = (best[i] == INFINITY) ? 0 : first_nan;
+                    idx_out[t] = r;
+                    if (dmin_out) dmin_out[t] = best[i];
+                }
             }
         }
     }
 }
 
+__global__ void __launch_bounds__(256)
+    fp32_finalize_kernel(const unsigned long long* __restrict__ keys, const int32_t* __restrict__ token_list,
+                         const int32_t* __restrict__ list_count, int64_t N, int K,
+                         const unsigned char* __restrict__ pack, int64_t* __restrict__ idx_out,
+                         float* __restrict__ dmin_out) {
+    const int64_t count = token_list ? (int64_t)(*list_count) : N;
+    const int first_nan = reinterpret_cast<const int*>(pack)[0];
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < count;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = token_list ? (int64_t)token_list[r] : r;
+        float d;
+        int idx;
+        key_unpack(keys[r], d, idx);
+        if (first_nan < K) idx = (d == INFINITY) ? 0 : first_nan;
+        idx_out[t] = idx;
+        if (dmin_out) dmin_out[t] = d;
+    }
+}
+
+size_t search_fp32_workspace_bytes(int64_t n_rows) { return 8 * (size_t)n_rows + 1024; }
+
+// keys_ws: scratch of search_fp32_workspace_bytes(rows) bytes, needed when the codebook is split
 int launch_search_fp32(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                        const void* pack, const int32_t* token_list, const int32_t* list_count,
-                       int64_t max_list, int64_t* idx_out, float* dmin_out, cudaStream_t s) {
+                       int64_t max_list, void* keys_ws, size_t keys_bytes, int64_t* idx_out,
+                       float* dmin_out, cudaStream_t s) {
     const int64_t N = B * HW;
     const int64_t rows = token_list ? max_list : N;
     if (rows <= 0) return VQB_OK;
-    const int64_t grid = (rows + kFtTokens - 1) / kFtTokens;
-    if (grid > 2147483647LL) {
-        set_error("too many tokens for one launch: %lld", (long long)rows);
-        return VQB_ERR_INVALID_ARG;
-    }
     const PackLayout L = pack_layout(K, D);
-    search_fp32_kernel<<<(unsigned)grid, kFtThreads, 0, s>>>(
-        z, N, D, HW, E, K, static_cast<const unsigned char*>(pack), L, token_list, list_count,
-        idx_out, dmin_out);
+    const int sms = sm_count();
+    const int64_t tiles = (rows + kFtTokens - 1) / kFtTokens;
+    const int code_tiles = (K + kFtCodes - 1) / kFtCodes;
+
+    // splits: a token list is short (re-score) -> spread each tile over the SMs; a dense run
+    // only splits when there are too few token tiles to fill the chip twice
+    int splits = 1;
+    if (token_list) {
+        splits = code_tiles < 32 ? code_tiles : 32;
+    } else if (tiles < 2 * sms) {
+        int64_t want = (2 * sms + tiles - 1) / tiles;
+        splits = (int)(want < code_tiles ? want : code_tiles);
+    }
+    if (splits < 1) splits = 1;
+    if (splits > 1 && (keys_ws == nullptr || keys_bytes < search_fp32_workspace_bytes(rows))) splits = 1;
+    const int tiles_per_split = (code_tiles + splits - 1) / splits;
+    const int codes_per_split = tiles_per_split * kFtCodes;
+    splits = (code_tiles + tiles_per_split - 1) / tiles_per_split;
+
+    unsigned long long* keys = nullptr;
+    if (splits > 1) {
+        keys = static_cast<unsigned long long*>(keys_ws);
+        VQB_CUDA_TRY(cudaMemsetAsync(keys, 0xff, 8 * (size_t)rows, s));
+    }
+    int64_t items = tiles * splits;
+    const int64_t cap = (int64_t)sms * 2 * (token_list ? 1 : 64);  // persistent for lists
+    const unsigned grid = (unsigned)(items < cap ? items : cap);
+    search_fp32_kernel<<<grid, kFtThreads, 0, s>>>(z, N, D, HW, E, K, static_cast<const unsigned char*>(pack),
+                                                   L, token_list, list_count, splits, codes_per_split, keys,
+                                                   idx_out, dmin_out);
     VQB_LAUNCH_CHECK("search_fp32_kernel");
+    if (splits > 1) {
+        int64_t fb = (rows + 255) / 256;
+        if (fb > (int64_t)sms * 8) fb = (int64_t)sms * 8;
+        fp32_finalize_kernel<<<(unsigned)fb, 256, 0, s>>>(keys, token_list, list_count, N, K,
+                                                         static_cast<const unsigned char*>(pack), idx_out,
+                                                         dmin_out);
+        VQB_LAUNCH_CHECK("fp32_finalize_kernel");
+    }
     return VQB_OK;
 }
 

@@ -3,8 +3,8 @@
 // (vqgan_ldm_baseline/models/quantizer.py:68-76).
 //
 // Design (DESIGN.md "search, low-D"):
-//  * one persistent CTA per SM, 256 threads; every thread owns T tokens whose
-//    negated coordinates sit in registers, duplicated into f32x2 pairs;
+//  * persistent CTAs (two per SM, 256 threads); every thread owns T tokens whose
+//    negated coordinates sit in registers;
 //  * the codebook streams through shared memory in tiles (1-D bulk-async copies
 //    completing on an mbarrier, double buffered) in a pair-interleaved layout so
 //    that one FFMA2 evaluates one coordinate of TWO codes for one token:
@@ -21,16 +21,32 @@
 
 namespace vqb {
 
-constexpr int kLowDThreads = 256;
 constexpr int kChunkCodes = 64;  // codes per index-tracking chunk (= 32 pairs, one per lane)
 
-template <int D>
+// launch shape variants (selected at run time by vqb_tune("lowd_variant", v); 0 is the default)
+//   V0: 256 threads x 2 CTA/SM, up to 8 tokens/thread (measured best: 47.5 TFLOP/s at D=4)
+//   V1: 256 x 1 CTA/SM, 8 tokens/thread (45.6)            V2: 512 x 1 CTA/SM, 4 tokens/thread (47.1)
+//   V3: 256 x 2 CTA/SM, 4 tokens/thread (44.5)            V4: 256 x 3 CTA/SM, 4 tokens/thread (42.9)
+template <int V>
+struct LowDVariant {
+    static constexpr int kThreads = V == 2 ? 512 : 256;
+    static constexpr int kMinBlocks = (V == 0 || V == 3) ? 2 : (V == 4 ? 3 : 1);
+    static constexpr int kTcap = (V >= 2) ? 4 : 8;
+};
+
+template <int D, int V>
 struct LowDCfg {
-    static constexpr int kTmax = D <= 4 ? 8 : (D <= 8 ? 4 : 2);
+    static constexpr int kThreads = LowDVariant<V>::kThreads;
+    static constexpr int kMinBlocks = LowDVariant<V>::kMinBlocks;
+    static constexpr int kTbase = D <= 4 ? 8 : (D <= 8 ? 4 : 2);
+    static constexpr int kTmax = kTbase < LowDVariant<V>::kTcap ? kTbase : LowDVariant<V>::kTcap;
     static constexpr int kTileCodes = D <= 4 ? 2048 : (D <= 8 ? 1024 : 512);
     static constexpr int kTileFloats = kTileCodes * (D + 1);
     static constexpr size_t kSmemBytes = 2 * sizeof(float) * kTileFloats + 64;
 };
+
+static int g_lowd_variant = 0;
+void set_lowd_variant(int v) { g_lowd_variant = v; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -66,7 +82,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         : "memory");
 }
 
-template <int D>
+template <int D, int V>
 struct LowDCtx {
     const float* z;
     int64_t N, HW;
@@ -83,25 +99,25 @@ struct LowDCtx {
     uint32_t total_visits;
 };
 
-template <int D>
-__device__ __forceinline__ int tile_codes(const LowDCtx<D>& c, int tile) {
-    const int left = c.codes_padded - tile * LowDCfg<D>::kTileCodes;
-    return left < LowDCfg<D>::kTileCodes ? left : LowDCfg<D>::kTileCodes;
+template <int D, int V>
+__device__ __forceinline__ int tile_codes(const LowDCtx<D, V>& c, int tile) {
+    const int left = c.codes_padded - tile * LowDCfg<D, V>::kTileCodes;
+    return left < LowDCfg<D, V>::kTileCodes ? left : LowDCfg<D, V>::kTileCodes;
 }
 
 // one thread: enqueue the bulk copies of tile-visit `v` into buffer v&1
-template <int D>
-__device__ __forceinline__ void issue_visit(const LowDCtx<D>& c, uint32_t v) {
+template <int D, int V>
+__device__ __forceinline__ void issue_visit(const LowDCtx<D, V>& c, uint32_t v) {
+    using Cfg = LowDCfg<D, V>;
     const int tile = v % c.n_tiles;
-    const int codes = tile_codes<D>(c, tile);
-    float* buf = c.smem_tiles + (v & 1) * LowDCfg<D>::kTileFloats;
+    const int codes = tile_codes<D, V>(c, tile);
+    float* buf = c.smem_tiles + (v & 1) * Cfg::kTileFloats;
     uint64_t* bar = c.bars + (v & 1);
     const uint32_t bytes_e = codes * D * sizeof(float);
     const uint32_t bytes_h = codes * sizeof(float);
     mbar_expect_tx(bar, bytes_e + bytes_h);
-    bulk_g2s(buf, c.g_pairs + (size_t)tile * LowDCfg<D>::kTileCodes * D, bytes_e, bar);
-    bulk_g2s(buf + LowDCfg<D>::kTileCodes * D, c.g_half_norm + (size_t)tile * LowDCfg<D>::kTileCodes,
-             bytes_h, bar);
+    bulk_g2s(buf, c.g_pairs + (size_t)tile * Cfg::kTileCodes * D, bytes_e, bar);
+    bulk_g2s(buf + Cfg::kTileCodes * D, c.g_half_norm + (size_t)tile * Cfg::kTileCodes, bytes_h, bar);
 }
 
 // score of one code pair for one token: D chained FFMA2 seeded with the half norms
@@ -130,10 +146,11 @@ __device__ __forceinline__ void load_pair(const float* p, unsigned long long (&e
     }
 }
 
-// T tokens per thread: tokens seg_base + t*256 + tid
-template <int D, int T>
-__device__ __forceinline__ void lowd_segment(LowDCtx<D>& c, int64_t seg_base) {
-    using Cfg = LowDCfg<D>;
+// T tokens per thread: tokens seg_base + t*kThreads + tid
+template <int D, int V, int T>
+__device__ __forceinline__ void lowd_segment(LowDCtx<D, V>& c, int64_t seg_base) {
+    using Cfg = LowDCfg<D, V>;
+    constexpr int kLowDThreads = Cfg::kThreads;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
 
@@ -166,7 +183,7 @@ __device__ __forceinline__ void lowd_segment(LowDCtx<D>& c, int64_t seg_base) {
         const uint32_t v = c.visit;
         const float* buf = c.smem_tiles + (v & 1) * Cfg::kTileFloats;
         mbar_wait(c.bars + (v & 1), (v >> 1) & 1);
-        const int chunks = tile_codes<D>(c, tile) / kChunkCodes;
+        const int chunks = tile_codes<D, V>(c, tile) / kChunkCodes;
         const float* hbuf = buf + Cfg::kTileCodes * D;
         for (int ch = 0; ch < chunks; ++ch) {
             const float* ep = buf + (size_t)ch * kChunkCodes * D;
@@ -192,7 +209,7 @@ __device__ __forceinline__ void lowd_segment(LowDCtx<D>& c, int64_t seg_base) {
         }
         __syncthreads();  // every warp is done with this buffer
         c.visit = v + 1;
-        if (tid == 0 && v + 2 < c.total_visits) issue_visit<D>(c, v + 2);
+        if (tid == 0 && v + 2 < c.total_visits) issue_visit<D, V>(c, v + 2);
     }
 
     // ---- resolve the index: the warp re-scores chunk cid[t] of each token ----
@@ -240,14 +257,15 @@ __device__ __forceinline__ void lowd_segment(LowDCtx<D>& c, int64_t seg_base) {
     }
 }
 
-template <int D>
-__global__ void __launch_bounds__(kLowDThreads, 1)
+template <int D, int V>
+__global__ void __launch_bounds__(LowDCfg<D, V>::kThreads, LowDCfg<D, V>::kMinBlocks)
     search_lowd_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int K,
                        const unsigned char* __restrict__ pack, PackLayout L, int64_t tokens_per_cta,
                        int64_t* __restrict__ idx_out, float* __restrict__ dmin_out) {
-    using Cfg = LowDCfg<D>;
+    using Cfg = LowDCfg<D, V>;
+    constexpr int kLowDThreads = Cfg::kThreads;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    LowDCtx<D> c;
+    LowDCtx<D, V> c;
     c.z = z;
     c.N = N;
     c.HW = HW;
@@ -279,48 +297,44 @@ __global__ void __launch_bounds__(kLowDThreads, 1)
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        issue_visit<D>(c, 0);
-        if (c.total_visits > 1) issue_visit<D>(c, 1);
+        issue_visit<D, V>(c, 0);
+        if (c.total_visits > 1) issue_visit<D, V>(c, 1);
     }
 
     int64_t base = start;
     while (q >= TM) {
-        lowd_segment<D, TM>(c, base);
+        lowd_segment<D, V, TM>(c, base);
         base += (int64_t)TM * kLowDThreads;
         q -= TM;
     }
     if constexpr (TM >= 8) {
         if (q & 4) {
-            lowd_segment<D, 4>(c, base);
+            lowd_segment<D, V, 4>(c, base);
             base += 4 * kLowDThreads;
         }
     }
     if constexpr (TM >= 4) {
         if (q & 2) {
-            lowd_segment<D, 2>(c, base);
+            lowd_segment<D, V, 2>(c, base);
             base += 2 * kLowDThreads;
         }
     }
-    if (q & 1) lowd_segment<D, 1>(c, base);
+    if (q & 1) lowd_segment<D, V, 1>(c, base);
 }
 
-template <int D>
+template <int D, int V>
 static int launch_lowd_t(const float* z, int64_t N, int64_t HW, int K, const void* pack,
                          int64_t* idx_out, float* dmin_out, cudaStream_t s) {
-    using Cfg = LowDCfg<D>;
-    static bool configured = false;  // attribute is per-function, idempotent
-    if (!configured) {
-        VQB_CUDA_TRY(cudaFuncSetAttribute(search_lowd_kernel<D>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)Cfg::kSmemBytes));
-        configured = true;
-    }
+    using Cfg = LowDCfg<D, V>;
+    constexpr int kLowDThreads = Cfg::kThreads;
+    VQB_CUDA_TRY(cudaFuncSetAttribute(search_lowd_kernel<D, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)Cfg::kSmemBytes));
     const PackLayout L = pack_layout(K, D);
-    const int sms = sm_count();
-    int64_t per_cta = (N + sms - 1) / sms;
+    const int slots = sm_count() * Cfg::kMinBlocks;  // persistent: one wave of resident CTAs
+    int64_t per_cta = (N + slots - 1) / slots;
     per_cta = (per_cta + kLowDThreads - 1) / kLowDThreads * kLowDThreads;
     const int grid = (int)((N + per_cta - 1) / per_cta);
-    search_lowd_kernel<D><<<grid, kLowDThreads, Cfg::kSmemBytes, s>>>(
+    search_lowd_kernel<D, V><<<grid, kLowDThreads, Cfg::kSmemBytes, s>>>(
         z, N, HW, K, static_cast<const unsigned char*>(pack), L, per_cta, idx_out, dmin_out);
     VQB_LAUNCH_CHECK("search_lowd_kernel");
     return VQB_OK;
@@ -329,10 +343,19 @@ static int launch_lowd_t(const float* z, int64_t N, int64_t HW, int K, const voi
 int launch_search_lowd(const float* z, int64_t B, int D, int64_t HW, int K, const void* pack,
                        int64_t* idx_out, float* dmin_out, cudaStream_t s) {
     const int64_t N = B * HW;
+    if (D == 4 && g_lowd_variant != 0) {  // tuning variants are only instantiated for the headline D
+        switch (g_lowd_variant) {
+            case 1: return launch_lowd_t<4, 1>(z, N, HW, K, pack, idx_out, dmin_out, s);
+            case 2: return launch_lowd_t<4, 2>(z, N, HW, K, pack, idx_out, dmin_out, s);
+            case 3: return launch_lowd_t<4, 3>(z, N, HW, K, pack, idx_out, dmin_out, s);
+            case 4: return launch_lowd_t<4, 4>(z, N, HW, K, pack, idx_out, dmin_out, s);
+            default: break;
+        }
+    }
     switch (D) {
 #define VQB_CASE(d) \
     case d:         \
-        return launch_lowd_t<d>(z, N, HW, K, pack, idx_out, dmin_out, s);
+        return launch_lowd_t<d, 0>(z, N, HW, K, pack, idx_out, dmin_out, s);
         VQB_CASE(1) VQB_CASE(2) VQB_CASE(3) VQB_CASE(4) VQB_CASE(5) VQB_CASE(6) VQB_CASE(7) VQB_CASE(8)
         VQB_CASE(9) VQB_CASE(10) VQB_CASE(11) VQB_CASE(12) VQB_CASE(13) VQB_CASE(14) VQB_CASE(15)
         VQB_CASE(16)

@@ -14,6 +14,29 @@ from . import _cabi
 from ._cabi import check, lib
 
 
+# measurement hooks used by bench.py: LAUNCHES counts libvqb200 kernel launches by entry
+# point; when PROFILE is a list, (start, stop) CUDA events bracketing the search launch on
+# the current stream are appended to it.
+LAUNCHES = {"total": 0}
+PROFILE = None
+_KERNELS_PER_CALL = {"prepare": 2, "search": 2, "tail": 2, "backward": 1, "gather": 1, "hist": 2,
+                     "code_sums": 1, "ema": 2, "keys": 1}
+
+
+def _count(kind: str, kernels: int = 0) -> None:
+    LAUNCHES["total"] += kernels or _KERNELS_PER_CALL[kind]
+    LAUNCHES[kind] = LAUNCHES.get(kind, 0) + 1
+
+
+def _search_kernels(D: int, algo: int) -> int:
+    """libvqb200 kernels one vqb_search_f32 call launches (mirrors resolve_algo in vqb_api.cu)."""
+    if algo == _cabi.ALGO_AUTO:
+        algo = (_cabi.ALGO_LOWD_FMA if D <= 16 else
+                _cabi.ALGO_TCGEN05 if (D % 64 == 0 and D <= 256) else _cabi.ALGO_FP32_TILE)
+    # lowd: search + stats; fp32: search (+ finalize) + stats; tcgen05: split, mma, re-score, finalize, stats
+    return {_cabi.ALGO_LOWD_FMA: 2, _cabi.ALGO_FP32_TILE: 3, _cabi.ALGO_TCGEN05: 5}[algo]
+
+
 def _p(t: Optional[Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -53,6 +76,7 @@ def _prepare(weight: Tensor) -> Tensor:
     pack = _bytes(nbytes, weight.device)
     check(lib().vqb_codebook_prepare_f32(_p(weight), K, D, _p(pack), nbytes, _stream()),
           "vqb_codebook_prepare_f32")
+    _count("prepare")
     return pack
 
 
@@ -65,8 +89,16 @@ def _search_into(z: Tensor, weight: Tensor, algo: int, want_dmin: bool):
     stats = torch.zeros(4, dtype=torch.int64, device=dev)
     ws_bytes = lib().vqb_search_workspace_bytes(B, D, HW, K, algo)
     ws = _bytes(ws_bytes, dev)
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     check(lib().vqb_search_f32(_p(z), B, D, HW, _p(weight), K, _p(pack), _p(idx), _p(dmin), _p(ws),
                                ws_bytes, algo, _p(stats), _stream()), "vqb_search_f32")
+    if prof is not None:
+        ev1.record()
+        prof.append((ev0, ev1))
+    _count("search", _search_kernels(D, algo))
     return idx, dmin, stats
 
 
@@ -80,6 +112,12 @@ def search(z: Tensor, weight: Tensor, algo: int = 0) -> Tuple[Tensor, Tensor, Te
     _need_cuda_f32(weight, "weight")
     z = z.contiguous()
     weight = weight.contiguous()
+    if z.numel() == 0:
+        shape = (z.shape[0],) + tuple(z.shape[2:])
+        _shape_bdhw(z, weight)
+        return (torch.empty(shape, dtype=torch.int64, device=z.device),
+                torch.empty(shape, dtype=torch.float32, device=z.device),
+                torch.zeros(4, dtype=torch.int64, device=z.device))
     with torch.cuda.device(z.device):
         idx, dmin, stats = _search_into(z, weight, algo, True)
     return idx, dmin, stats
@@ -106,6 +144,11 @@ def quantize(z: Tensor, weight: Tensor, beta: float, algo: int = 0
     z = z.contiguous()
     weight = weight.contiguous()
     B, D, HW, K = _shape_bdhw(z, weight)
+    if B * HW == 0:  # nothing to launch; mean over zero elements is NaN like F.mse_loss
+        nan = torch.full((), float("nan"), device=z.device)
+        return (torch.empty_like(z), nan, nan.clone(),
+                torch.empty((B,) + tuple(z.shape[2:]), dtype=torch.int64, device=z.device),
+                torch.zeros(4, dtype=torch.int64, device=z.device))
     with torch.cuda.device(z.device):
         idx, _, stats = _search_into(z, weight, algo, False)
         z_q = torch.empty_like(z)
@@ -115,6 +158,7 @@ def quantize(z: Tensor, weight: Tensor, beta: float, algo: int = 0
         check(lib().vqb_gather_loss_st_f32(_p(z), _p(weight), _p(idx), B, D, HW, K, float(beta),
                                            _p(z_q), _p(loss), _p(partials), pbytes, None, _stream()),
               "vqb_gather_loss_st_f32")
+        _count("tail")
     return z_q, loss[1].clone(), loss[0].clone(), idx, stats
 
 
@@ -137,12 +181,15 @@ def quantize_backward(z: Tensor, weight: Tensor, indices: Tensor, g_zq: Optional
         g_zq = g_zq.contiguous().to(torch.float32)
     if g_vq is not None:
         g_vq = g_vq.reshape(1).to(torch.float32).contiguous()
+    if z.numel() == 0:
+        return torch.empty_like(z), (torch.zeros_like(weight) if need_dE else weight.new_empty((0,)))
     with torch.cuda.device(z.device):
         dz = torch.empty_like(z)
         dE = torch.zeros_like(weight) if need_dE else None
         check(lib().vqb_backward_f32(_p(z), _p(weight), _p(indices), _p(g_zq), _p(g_vq), float(beta),
                                      B, D, HW, K, _p(dz), _p(dE), None, _stream()),
               "vqb_backward_f32")
+        _count("backward")
     if dE is None:
         dE = weight.new_empty((0,))
     return dz, dE
@@ -185,9 +232,12 @@ def codebook_entry(weight: Tensor, indices: Tensor) -> Tuple[Tensor, Tensor]:
     HW = indices.numel() // max(B, 1) if B > 0 else 0
     out = torch.empty((B, D) + tuple(indices.shape[1:]), dtype=torch.float32, device=weight.device)
     err = torch.zeros(1, dtype=torch.int32, device=weight.device)
+    if indices.numel() == 0:
+        return out, err
     with torch.cuda.device(weight.device):
         check(lib().vqb_gather_f32(_p(weight), _p(indices), B, D, HW, K, _p(out), _p(err), _stream()),
               "vqb_gather_f32")
+        _count("gather")
     return out, err
 
 
@@ -209,6 +259,7 @@ def codebook_usage(indices: Tensor, num_embeddings: int) -> Tuple[Tensor, Tensor
     with torch.cuda.device(indices.device):
         check(lib().vqb_hist_i64(_p(indices), indices.numel(), num_embeddings, _p(hist), _p(used),
                                  _p(err), _stream()), "vqb_hist_i64")
+        _count("hist")
     return hist, used, err
 
 
