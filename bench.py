@@ -259,7 +259,7 @@ def run_gpu_arm(args):
     barrier()
 
     # ---- device-resident timing: exactly K steps between two events --------
-    ops.PROFILE = []
+    ops.PROFILE, ops.PROFILE_TAIL, ops.PROFILE_BWD = [], [], []
     launches0 = ops.LAUNCHES["total"]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
@@ -272,7 +272,9 @@ def run_gpu_arm(args):
     ms_total = ev0.elapsed_time(ev1)
     gpu_launches = ops.LAUNCHES["total"] - launches0
     search_ms = [a.elapsed_time(b) for a, b in ops.PROFILE]
-    ops.PROFILE = None
+    tail_ms = [a.elapsed_time(b) for a, b in ops.PROFILE_TAIL]
+    bwd_ms = [a.elapsed_time(b) for a, b in ops.PROFILE_BWD]
+    ops.PROFILE = ops.PROFILE_TAIL = ops.PROFILE_BWD = None
     if world > 1:
         t = torch.tensor([ms_total], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -286,8 +288,24 @@ def run_gpu_arm(args):
     vq_sync = VectorQuantizer(K, D, BETA).to(device)
     vq_sync.embedding.weight = weight
 
-    def e2e_step(i):
-        z = z_host[i % 2].to(device, non_blocking=True).requires_grad_(True)
+    # input pipeline like a training loop's data loader: the NEXT step's latents are copied
+    # host->device on a side stream while the current step computes (every step still pays
+    # its own H2D copy and D2H read-back inside the timed region)
+    copy_stream = torch.cuda.Stream(device=device)
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            zt = z_host[i % 2].to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return zt, ev
+
+    def e2e_step(i, staged):
+        zt, ev = staged
+        torch.cuda.current_stream().wait_event(ev)
+        zt.record_stream(torch.cuda.current_stream())
+        nxt = prefetch(i + 1)
+        z = zt.requires_grad_(True)
         weight.grad = None
         z_q, loss_dict, idx = vq_sync(z)  # reference contract: Python floats in loss_dict (host sync)
         (loss_dict["vq_loss"] + (z_q * gs[i % len(gs)]).sum()).backward()
@@ -297,16 +315,17 @@ def run_gpu_arm(args):
             dE, hist, s = vdist.allreduce_stats(weight.grad, usage, sq, average_dE=True)
             weight.grad.copy_(dE)
         idx_host.copy_(idx, non_blocking=True)
-        return loss_dict["vq_loss"].item()
+        return loss_dict["vq_loss"].item(), nxt
 
     e2e_steps = max(3, min(args.steps, 20))
+    staged = prefetch(0)
     for i in range(3):
-        e2e_step(i)
+        _, staged = e2e_step(i, staged)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(e2e_steps):
-        e2e_step(i)
+        _, staged = e2e_step(3 + i, staged)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -332,9 +351,19 @@ def run_gpu_arm(args):
                                                3: "search_tc_kernel"}.get(algo, str(algo)),
                     "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                     "traffic": None, "kernel_ms": s_ms, "algorithmic_flops_per_launch": flops,
+                    "executed_flops_factor": 3 if algo == 3 else 1,
+                    "frac_executed": achieved * (3 if algo == 3 else 1) / peak,
                     "peak_source": peak_note,
                     "step_share": s_ms * len(search_ms) / ms_total if search_ms else None}
-        # HBM-side kernels (tail + backward): algorithmic bytes per token 8D+8 and 12D+8
+        # HBM-side kernels: algorithmic bytes per token 8D+8 (tail) and 12D+8 (+ dE once) (backward)
+        hbm = {}
+        for name, ms_list, nbytes in (("gather_loss_st_kernel", tail_ms, tokens * (8 * D + 8)),
+                                      ("backward_kernel", bwd_ms, tokens * (12 * D + 8) + 4 * K * D)):
+            if ms_list:
+                t = statistics.mean(ms_list)
+                hbm[name] = {"kernel_ms": t, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (t * 1e-3) / 1e9,
+                             "peak_gbs": peaks["hbm_gbs"], "frac": nbytes / (t * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                             "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})"}
         line = {
             "metric": "vq_lookup_tokens_per_sec", "value": tokens * world * args.steps / (ms_total * 1e-3),
             "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -349,8 +378,9 @@ def run_gpu_arm(args):
             "e2e": {"value": tokens * world * e2e_steps / (e2e_ms * 1e-3), "unit": "tokens/s",
                     "h2d_bytes_per_step": zs[0].numel() * 4, "d2h_bytes_per_step": tokens * 8 + 8,
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                    "api": "VectorQuantizer.forward + backward on pinned host latents, indices and loss read back"},
+                    "api": "VectorQuantizer.forward + backward on pinned host latents (H2D of step i+1 overlaps step i on a copy stream), indices and loss read back every step"},
             "gpu_launches": gpu_launches,
+            "hbm_kernels": hbm,
             "clocks": clk.summary(),
             "fma_peak_tflops": {"scalar": fma_scalar, "packed": fma_packed},
         }

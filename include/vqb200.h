@@ -138,6 +138,11 @@ VQB_API int vqb_unpack_argmin_keys(const int64_t* keys, int64_t n, int64_t* idx_
 VQB_API int vqb_fma_peak_launch(int packed, int iters, float* sink, double* flops_host,
                         vqb_stream_t stream);
 
+/* instruction-mix microbenchmarks of the low-D inner loop (modes in csrc/vqb_ubench.cu);
+ * src: >= 10240 floats of finite data */
+VQB_API int vqb_ubench_launch(int mode, int sweeps, const float* src, float* sink, double* flops_host,
+                      vqb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,74 @@
+"""Summarises ncu outputs into small text files for profiles/ (run in the build container).
+
+    python scripts/summarize_ncu.py rep  gpurun_out/x.ncu-rep  profiles/out.txt
+    python scripts/summarize_ncu.py list gpurun_out/launches.csv profiles/out.txt
+"""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "derived__sm__sass_thread_inst_executed_op_ffma_pred_on_x2",
+    "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+]
+
+
+def rep(path, out):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    with open(out, "w") as f:
+        f.write(f"# ncu --set full --clock-control none; source: {path}\n")
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            f.write(f"\n## {d.get('Kernel Name', '?')}  grid={d.get('Grid Size')} block={d.get('Block Size')}\n")
+            for k in KEYS:
+                if k in d:
+                    f.write(f"{k:90s} {units[hdr.index(k)]:16s} {d[k]}\n")
+
+
+def launches(path, out):
+    rows = list(csv.DictReader(l for l in open(path) if l.startswith('"')))
+    agg = collections.OrderedDict()
+    for r in rows:
+        name = r["Kernel Name"]
+        short = name.split("(")[0].replace("void ", "") if "vqb" in name or "write_stats" in name else \
+            "torch: " + name.split("(")[0][-60:]
+        a = agg.setdefault(short, [0, 0.0])
+        a[0] += 1
+        a[1] += float(r["Metric Value"])
+    tot = sum(v[1] for v in agg.values())
+    with open(out, "w") as f:
+        f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none; source: {path}\n")
+        f.write("# per-launch times are cold-cache and serialised: compare shares, not absolutes\n")
+        f.write(f"# {len(rows)} launches, {tot / 1e6:.3f} ms total\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{v[1] / 1e6:10.3f} ms {100 * v[1] / tot:6.2f}% {v[0]:5d}x avg {v[1] / v[0] / 1e3:10.1f} us  {k}\n")
+
+
+if __name__ == "__main__":
+    {"rep": rep, "list": launches}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -1,0 +1,117 @@
+// Instruction-mix microbenchmarks behind the low-D search design (DESIGN.md "FMA roofline").
+// Each mode replays the inner loop of search_lowd_kernel<4> on one 2048-code tile held in shared
+// memory, with parts of the instruction mix removed, so the cost of each ingredient can be read
+// off the B200 directly:
+//   mode 0  FFMA2 chains only (accumulators never reset; no minimum)
+//   mode 1  FFMA2 + FMNMX3 (the shipped mix)
+//   mode 2  scalar FFMA chains only
+//   mode 3  scalar FFMA + FMNMX3
+// flops reported = 2 * 4 dims * tokens * codes (the algorithmic count of the search).
+#include "vqb_common.cuh"
+
+namespace vqb {
+
+constexpr int kUbCodes = 2048;
+
+template <int MODE, int T>
+__global__ void __launch_bounds__(256, 2) ubench_kernel(int sweeps, const float* __restrict__ src, float* sink) {
+    __shared__ __align__(16) float tile[kUbCodes * 5];
+    for (int i = threadIdx.x; i < kUbCodes * 5; i += blockDim.x) tile[i] = src[i];
+    __syncthreads();
+    float m[T];
+    float nzs[T][4];
+    unsigned long long nz[T][4];
+    unsigned long long acc2[T];
+    float accs[T][2];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        m[t] = INFINITY;
+        acc2[t] = 0ull;
+        accs[t][0] = accs[t][1] = 0.f;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            nzs[t][d] = src[(threadIdx.x * T + t) * 4 + d];
+            nz[t][d] = pack_f32x2(nzs[t][d], nzs[t][d]);
+        }
+    }
+    const float* hbuf = tile + kUbCodes * 4;
+    for (int s = 0; s < sweeps; ++s) {
+#pragma unroll 4
+        for (int p = 0; p < kUbCodes / 2; ++p) {
+            const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(tile + p * 8);
+            const ulonglong2 v1 = *reinterpret_cast<const ulonglong2*>(tile + p * 8 + 4);
+            const unsigned long long h2 = *reinterpret_cast<const unsigned long long*>(hbuf + 2 * p);
+            if constexpr (MODE == 0 || MODE == 1) {
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    unsigned long long a = fma_f32x2(nz[t][0], v0.x, MODE == 1 ? h2 : acc2[t]);
+                    a = fma_f32x2(nz[t][1], v0.y, a);
+                    a = fma_f32x2(nz[t][2], v1.x, a);
+                    a = fma_f32x2(nz[t][3], v1.y, a);
+                    if constexpr (MODE == 1) {
+                        float x, y;
+                        unpack_f32x2(a, x, y);
+                        m[t] = min3_f32(m[t], x, y);
+                    } else {
+                        acc2[t] = a;
+                    }
+                }
+            } else {
+                float e[8], h[2];
+                unpack_f32x2(v0.x, e[0], e[1]);
+                unpack_f32x2(v0.y, e[2], e[3]);
+                unpack_f32x2(v1.x, e[4], e[5]);
+                unpack_f32x2(v1.y, e[6], e[7]);
+                unpack_f32x2(h2, h[0], h[1]);
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    float a0 = fmaf(nzs[t][0], e[0], MODE == 3 ? h[0] : accs[t][0]);
+                    float a1 = fmaf(nzs[t][0], e[1], MODE == 3 ? h[1] : accs[t][1]);
+#pragma unroll
+                    for (int d = 1; d < 4; ++d) {
+                        a0 = fmaf(nzs[t][d], e[2 * d], a0);
+                        a1 = fmaf(nzs[t][d], e[2 * d + 1], a1);
+                    }
+                    if constexpr (MODE == 3) {
+                        m[t] = min3_f32(m[t], a0, a1);
+                    } else {
+                        accs[t][0] = a0;
+                        accs[t][1] = a1;
+                    }
+                }
+            }
+        }
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        float x, y;
+        unpack_f32x2(acc2[t], x, y);
+        r += m[t] + x + y + accs[t][0] + accs[t][1];
+    }
+    if (r == 123.456f) sink[0] = r;
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" int vqb_ubench_launch(int mode, int sweeps, const float* src, float* sink, double* flops_host,
+                                 vqb_stream_t stream) {
+    if (mode < 0 || mode > 3 || sweeps <= 0 || !src || !sink) {
+        set_error("vqb_ubench_launch: invalid argument");
+        return VQB_ERR_INVALID_ARG;
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int blocks = sm_count() * 2;
+    constexpr int T = 8;
+    switch (mode) {
+        case 0: ubench_kernel<0, T><<<blocks, 256, 0, s>>>(sweeps, src, sink); break;
+        case 1: ubench_kernel<1, T><<<blocks, 256, 0, s>>>(sweeps, src, sink); break;
+        case 2: ubench_kernel<2, T><<<blocks, 256, 0, s>>>(sweeps, src, sink); break;
+        default: ubench_kernel<3, T><<<blocks, 256, 0, s>>>(sweeps, src, sink); break;
+    }
+    VQB_LAUNCH_CHECK("ubench_kernel");
+    if (flops_host) *flops_host = 2.0 * 4 * (double)blocks * 256 * T * kUbCodes * sweeps;
+    return VQB_OK;
+}

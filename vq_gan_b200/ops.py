@@ -16,9 +16,12 @@ from ._cabi import check, lib
 
 # measurement hooks used by bench.py: LAUNCHES counts libvqb200 kernel launches by entry
 # point; when PROFILE is a list, (start, stop) CUDA events bracketing the search launch on
-# the current stream are appended to it.
+# the current stream are appended to it; PROFILE_TAIL / PROFILE_BWD do the same for the
+# forward-tail and backward launches.
 LAUNCHES = {"total": 0}
 PROFILE = None
+PROFILE_TAIL = None
+PROFILE_BWD = None
 _KERNELS_PER_CALL = {"prepare": 2, "search": 2, "tail": 2, "backward": 1, "gather": 1, "hist": 2,
                      "code_sums": 1, "ema": 2, "keys": 1}
 
@@ -155,9 +158,16 @@ def quantize(z: Tensor, weight: Tensor, beta: float, algo: int = 0
         loss = torch.empty(2, dtype=torch.float32, device=z.device)
         pbytes = lib().vqb_tail_partials_bytes(B * HW)
         partials = _bytes(pbytes, z.device)
+        prof = PROFILE_TAIL
+        if prof is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         check(lib().vqb_gather_loss_st_f32(_p(z), _p(weight), _p(idx), B, D, HW, K, float(beta),
                                            _p(z_q), _p(loss), _p(partials), pbytes, None, _stream()),
               "vqb_gather_loss_st_f32")
+        if prof is not None:
+            ev1.record()
+            prof.append((ev0, ev1))
         _count("tail")
     return z_q, loss[1].clone(), loss[0].clone(), idx, stats
 
@@ -186,9 +196,16 @@ def quantize_backward(z: Tensor, weight: Tensor, indices: Tensor, g_zq: Optional
     with torch.cuda.device(z.device):
         dz = torch.empty_like(z)
         dE = torch.zeros_like(weight) if need_dE else None
+        prof = PROFILE_BWD
+        if prof is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         check(lib().vqb_backward_f32(_p(z), _p(weight), _p(indices), _p(g_zq), _p(g_vq), float(beta),
                                      B, D, HW, K, _p(dz), _p(dE), None, _stream()),
               "vqb_backward_f32")
+        if prof is not None:
+            ev1.record()
+            prof.append((ev0, ev1))
         _count("backward")
     if dE is None:
         dE = weight.new_empty((0,))
