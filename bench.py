@@ -27,8 +27,12 @@ WORKLOADS = {
     "c2": (1024, 4, 32, 32, 16384, "low-dim f=4 LDM latent: 1M tokens x d=4 x codebook 16384, fwd+bwd"),
     "c3": (1024, 256, 32, 32, 16384, "high-dim tokenizer: 1M tokens x d=256 x codebook 16384, fwd+bwd"),
     "c1": (4, 256, 32, 32, 128, "train_vqgan.py default: 4096 tokens x d=256 x codebook 128, fwd+bwd"),
+    "c4": (64, 256, 32, 32, 128, "quantizer of the 256x256 VQ-GAN step, global batch 64 split over the ranks, "
+                                 "K=128 d=256, fwd+bwd + stats all-reduce (encoder/decoder out of scope)"),
+    "c5": (56, 256, 32, 32, 65536, "bulk encode: 56 images (57344 tokens) per rank per step, codebook 65536 x d=256 "
+                                   "sharded over the ranks, all-gather + local search + MIN reduce-scatter"),
 }
-CPU_CHUNK_TOKENS = {"c2": 32768, "c3": 16384, "c1": 4096}
+CPU_CHUNK_TOKENS = {"c2": 32768, "c3": 16384, "c1": 4096, "c4": 4096, "c5": 4096}
 BETA = 0.25
 N_ROTATE = 8  # distinct input sets cycled through so the working set exceeds the 126 MB L2
 
@@ -200,6 +204,77 @@ def gpu_strawman_tokens_per_s(workload, device):
     return B * H * W * 5 / (a.elapsed_time(b) * 1e-3)
 
 
+def run_sharded_encode(args, world, rank, local_rank, device, B, D, H, W, K, desc, peaks):
+    """c5: search only (encode_to_indices), codebook rows sharded over the ranks."""
+    import torch.distributed as dist
+    from vq_gan_b200 import ops
+    from vq_gan_b200 import distributed as vdist
+    tokens = B * H * W
+    klo, khi = vdist.shard_range(K, world, rank)
+    E = torch.randn(K, D, generator=torch.Generator().manual_seed(1))[klo:khi].contiguous().to(device)
+    gen = torch.Generator(device=device).manual_seed(100 + rank)
+    zs = [torch.randn(B, D, H, W, device=device, generator=gen) for _ in range(4)]
+
+    def step(i):
+        if world > 1:
+            return vdist.sharded_search_dp(zs[i % 4], E, klo)
+        idx, dmin, _ = ops.search(zs[i % 4], E)
+        return idx, dmin
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    warmup = max(args.warmup, 3)
+    for i in range(warmup):
+        step(i)
+    barrier()
+    launches0 = ops.LAUNCHES["total"]
+    ops.PROFILE = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            step(i)
+        ev1.record()
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    search_ms = [a.elapsed_time(b) for a, b in ops.PROFILE]
+    ops.PROFILE = None
+    if world > 1:
+        t = torch.tensor([ms_total], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    if rank == 0:
+        s_ms = statistics.mean(search_ms)
+        flops = 2.0 * tokens * world * (khi - klo) * D  # per-rank search: all tokens x local codes
+        achieved = flops / (s_ms * 1e-3) / 1e12
+        line = {
+            "metric": "vq_lookup_tokens_per_sec", "value": tokens * world * args.steps / (ms_total * 1e-3),
+            "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"c5: {desc}", "tokens_per_gpu_per_step": tokens, "D": D, "K": K,
+                       "codes_per_rank": khi - klo, "parallelism": f"codebook-sharded x{world}",
+                       "l2": "codebook shard (bf16 hi+lo) and 4 rotating latent sets exceed the 126 MB L2"},
+            "roofline": {"bound": "tensor", "kernel": "search_tc_kernel", "achieved": achieved,
+                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_tflops_sustained"], "executed_flops_factor": 3,
+                         "frac_executed": 3 * achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "kernel_ms": s_ms, "algorithmic_flops_per_launch": flops,
+                         "step_share": s_ms * len(search_ms) / ms_total},
+            "exchange_bytes_per_step": {"all_gather_latents": tokens * D * 4 * max(world - 1, 0),
+                                        "reduce_scatter_keys": tokens * world * 8 if world > 1 else 0},
+            "gpu_launches": ops.LAUNCHES["total"] - launches0, "clocks": clk.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+        dist.destroy_process_group()
+
+
 def run_gpu_arm(args):
     import torch.distributed as dist
     from vq_gan_b200 import VectorQuantizer, ops
@@ -214,15 +289,19 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=device)
 
     B, D, H, W, K, desc = WORKLOADS[args.workload]
+    if args.workload == "c4":
+        B = max(B // world, 1)  # global batch 64 split over the ranks (strong scaling of one step)
     tokens = B * H * W
     peaks = load_peaks()
+    if args.workload == "c5":
+        return run_sharded_encode(args, world, rank, local_rank, device, B, D, H, W, K, desc, peaks)
 
     vq = VectorQuantizer(K, D, BETA, lazy_stats=True).to(device)
     with torch.no_grad():
         vq.embedding.weight.copy_(torch.randn(K, D, generator=torch.Generator().manual_seed(1)))
     weight = vq.embedding.weight
 
-    n_rot = N_ROTATE if args.workload == "c2" else (2 if args.workload == "c3" else 64)
+    n_rot = N_ROTATE if args.workload == "c2" else (2 if args.workload == "c3" else 16)
     gen = torch.Generator(device=device).manual_seed(100 + rank)
     zs = [torch.randn(B, D, H, W, device=device, generator=gen).requires_grad_(True) for _ in range(n_rot)]
     gs = [torch.randn(B, D, H, W, device=device, generator=gen) for _ in range(min(n_rot, 2))]

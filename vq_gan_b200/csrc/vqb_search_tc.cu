@@ -381,6 +381,31 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
 }
 
+// exact fp32 score of the chosen code (same fmaf order as search_fp32_kernel, so the value is
+// bit-identical to what that kernel reports): makes dmin comparable across codebook shards
+__global__ void __launch_bounds__(256)
+    exact_score_kernel(const float* __restrict__ z, const float* __restrict__ E, const float* __restrict__ half_norm,
+                       const int64_t* __restrict__ idx, int64_t N, int D, int64_t HW, int K,
+                       float* __restrict__ dmin_out) {
+    const int64_t tok = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tok >= N) return;
+    int64_t k = idx[tok];
+    if (k < 0 || k >= K) k = 0;
+    const int64_t b = tok / HW;
+    const float* zp = z + (b * D) * HW + (tok - b * HW);
+    const float4* erow = reinterpret_cast<const float4*>(E + (size_t)k * D);
+    float acc = 0.f;
+    for (int d = 0; d < D; d += 4) {
+        const float4 e = __ldg(erow + (d >> 2));
+        acc = fmaf(__ldg(zp + (int64_t)(d + 0) * HW), e.x, acc);
+        acc = fmaf(__ldg(zp + (int64_t)(d + 1) * HW), e.y, acc);
+        acc = fmaf(__ldg(zp + (int64_t)(d + 2) * HW), e.z, acc);
+        acc = fmaf(__ldg(zp + (int64_t)(d + 3) * HW), e.w, acc);
+    }
+    const float d = half_norm[k] - acc;
+    dmin_out[tok] = (d != d) ? INFINITY : d;  // all-NaN rows report +inf like the fp32 kernel
+}
+
 __global__ void tc_stats_kernel(int64_t* stats, const int32_t* count) {
     stats[0] = *count;
     stats[1] = VQB_ALGO_TCGEN05;
@@ -532,6 +557,11 @@ int launch_search_tc(const float* z, int64_t B, int D, int64_t HW, const float* 
     rc = launch_search_fp32(z, B, D, HW, E, K, pack, list, count, N, wsb + w.off_keys, w.keys_bytes, idx_out,
                             dmin_out, s);
     if (rc != VQB_OK) return rc;
+    if (dmin_out) {
+        exact_score_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(z, E, p.half_norm, idx_out, N, D, HW, K,
+                                                                      dmin_out);
+        VQB_LAUNCH_CHECK("exact_score_kernel");
+    }
     if (stats_out) {
         tc_stats_kernel<<<1, 1, 0, s>>>(stats_out, count);
         VQB_LAUNCH_CHECK("tc_stats_kernel");

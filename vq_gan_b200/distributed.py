@@ -89,3 +89,26 @@ def sharded_search(z: torch.Tensor, weight_shard: torch.Tensor, index_offset: in
     keys = ops.pack_argmin_keys(dmin, idx, int(index_offset))
     reduce_argmin_keys(keys, group)
     return ops.unpack_argmin_keys(keys)
+
+
+def sharded_search_dp(z_local: torch.Tensor, weight_shard: torch.Tensor, index_offset: int, group=None,
+                      algo: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Codebook-sharded search when every rank holds DIFFERENT tokens (bulk encode,
+    `preprocess_latents.py`-style loop with `VQVAE.encode_to_indices`):
+
+      1. all-gather the latents  [B_r, D, ...] -> [R*B_r, D, ...]   (the one real exchange)
+      2. local search of this rank's codebook rows for all R*B_r*HW tokens
+      3. pack (score, global index) keys, MIN reduce-scatter so each rank receives the
+         winners of its own tokens only
+    Every rank must pass the same B_r.  Returns (global indices, min score) of the local tokens."""
+    from . import ops
+    world = dist.get_world_size(group)
+    z_local = z_local.contiguous()
+    gathered = torch.empty((world * z_local.shape[0],) + tuple(z_local.shape[1:]), dtype=z_local.dtype,
+                           device=z_local.device)
+    dist.all_gather_into_tensor(gathered, z_local, group=group)
+    idx, dmin, _ = ops.search(gathered, weight_shard, algo)
+    keys = ops.pack_argmin_keys(dmin, idx, int(index_offset))
+    mine = torch.empty((z_local.shape[0],) + tuple(keys.shape[1:]), dtype=torch.int64, device=keys.device)
+    dist.reduce_scatter_tensor(mine, keys, op=dist.ReduceOp.MIN, group=group)
+    return ops.unpack_argmin_keys(mine)
