@@ -11,9 +11,10 @@ from vq_gan_b200 import _cabi, ops  # noqa: E402
 lib = _cabi.lib()
 src = torch.randn(1 << 16, device="cuda")
 sink = torch.zeros(1, device="cuda")
-names = {0: "FFMA2 only", 1: "FFMA2 + FMNMX3 (shipped mix)", 2: "FFMA only", 3: "FFMA + FMNMX3"}
+names = {0: "FFMA2 only", 1: "FFMA2 + FMNMX3 (shipped mix)", 2: "FFMA only", 3: "FFMA + FMNMX3",
+         4: "FFMA2 + 2x FMNMX", 5: "FFMA2 + FMNMX3 one pair late"}
 print(f"fma peak: scalar {ops.fma_peak_tflops(False):.1f} packed {ops.fma_peak_tflops(True):.1f} TFLOP/s")
-for mode in range(4):
+for mode in range(6):
     best = 0.0
     for _ in range(4):
         flops = ctypes.c_double(0)

@@ -178,6 +178,173 @@ __global__ void __launch_bounds__(kTailThreads)
 }
 
 // ---------------------------------------------------------------------------
+// D % 64 == 0: shared-memory transposed variants.  A CTA owns 32 consecutive tokens and up to
+// 256 channels at a time: codebook rows are read as full 128-byte lines (lane = channel),
+// transposed through a conflict-free [channels][33] tile, and combined with z / g in the
+// token-major (lane = token) orientation in which z, z_q, dz are coalesced.  The dE scatter goes
+// back through the same tile so each token row leaves as float4 reductions on consecutive
+// addresses.  Two barriers per 256 channels; every thread keeps 16-32 loads in flight.
+// ---------------------------------------------------------------------------
+constexpr int kTileTok = 32;
+constexpr int kTileDimMax = 256;
+
+struct TileTokens {
+    int64_t off[kTileTok];  // element offset of (token, channel 0); -1 for tokens past N
+    int code[kTileTok];
+};
+
+__device__ __forceinline__ void tile_load_tokens(TileTokens& tt, const int64_t* __restrict__ idx, int64_t N,
+                                                 int D, int64_t HW, int K, int* err_flag) {
+    if (threadIdx.x < kTileTok) {
+        const int64_t tok = (int64_t)blockIdx.x * kTileTok + threadIdx.x;
+        int64_t off = -1;
+        int k = 0;
+        if (tok < N) {
+            int64_t kk = idx[tok];
+            if (kk < 0 || kk >= K) {
+                if (err_flag) *err_flag = 1;
+                kk = 0;
+            }
+            k = (int)kk;
+            const int64_t b = tok / HW;
+            off = (b * D) * HW + (tok - b * HW);
+        }
+        tt.off[threadIdx.x] = off;
+        tt.code[threadIdx.x] = k;
+    }
+}
+
+// codebook rows of the CTA's 32 tokens, channels [d0, d0+dc) -> tile[channel][token]
+__device__ __forceinline__ void tile_fill_codes(float (*tile)[kTileTok + 1], const TileTokens& tt,
+                                                const float* __restrict__ E, int D, int d0, int dc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = warp * 4 + i;
+        const float* erow = E + (size_t)tt.code[t] * D + d0;
+#pragma unroll 8
+        for (int c = lane; c < dc; c += 32) tile[c][t] = __ldg(erow + c);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    gather_loss_st_tiled_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                const int64_t* __restrict__ idx, int64_t N, int D, int64_t HW, int K,
+                                float* __restrict__ zq_out, double* __restrict__ partials,
+                                int* __restrict__ err_flag) {
+    __shared__ float tile[kTileDimMax][kTileTok + 1];
+    __shared__ TileTokens tt;
+    __shared__ double warp_part[8];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    tile_load_tokens(tt, idx, N, D, HW, K, err_flag);
+    __syncthreads();
+    const int64_t off = tt.off[tx];
+    float sq = 0.f;
+    for (int d0 = 0; d0 < D; d0 += kTileDimMax) {
+        const int dc = (D - d0) < kTileDimMax ? (D - d0) : kTileDimMax;
+        if (d0 > 0) __syncthreads();
+        tile_fill_codes(tile, tt, E, D, d0, dc);
+        __syncthreads();
+        if (off >= 0) {
+            for (int c0 = 0; c0 < dc; c0 += 128) {  // 16 channels per thread per round
+                float zv[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = c0 + ty + 8 * i;
+                    zv[i] = c < dc ? __ldg(z + off + (int64_t)(d0 + c) * HW) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = c0 + ty + 8 * i;
+                    if (c < dc) {
+                        const float diff = __fsub_rn(tile[c][tx], zv[i]);
+                        zq_out[off + (int64_t)(d0 + c) * HW] = __fadd_rn(zv[i], diff);
+                        sq = fmaf(diff, diff, sq);
+                    }
+                }
+            }
+        }
+    }
+    double v = warp_sum_f64((double)sq);
+    if (tx == 0) warp_part[ty] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += warp_part[w];
+        partials[blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    backward_tiled_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                          const int64_t* __restrict__ idx, const float* __restrict__ g_zq,
+                          const float* __restrict__ g_vq, float beta, float norm, int64_t N, int D,
+                          int64_t HW, int K, float* __restrict__ dz_out, float* __restrict__ dE,
+                          unsigned long long* __restrict__ hist) {
+    __shared__ float tile[kTileDimMax][kTileTok + 1];
+    __shared__ TileTokens tt;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int lane = tx, warp = ty;
+    tile_load_tokens(tt, idx, N, D, HW, K, nullptr);
+    __syncthreads();
+    const int64_t off = tt.off[tx];
+    const float gv = g_vq ? __ldg(g_vq) : 0.f;
+    const float gbeta = __fmul_rn(gv, beta);
+    if (hist != nullptr && ty == 0) {
+        const bool live = off >= 0;
+        const unsigned active = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const int k = tt.code[tx];
+            const unsigned peers = __match_any_sync(active, k);
+            if (lane == __ffs(peers) - 1) atomicAdd(hist + k, (unsigned long long)__popc(peers));
+        }
+    }
+    for (int d0 = 0; d0 < D; d0 += kTileDimMax) {
+        const int dc = (D - d0) < kTileDimMax ? (D - d0) : kTileDimMax;
+        if (d0 > 0) __syncthreads();
+        tile_fill_codes(tile, tt, E, D, d0, dc);
+        __syncthreads();
+        if (off >= 0) {
+            for (int c0 = 0; c0 < dc; c0 += 64) {  // 8 channels per thread per round, z and g
+                float zv[8], gz[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = c0 + ty + 8 * i;
+                    const int64_t o = off + (int64_t)(d0 + c) * HW;
+                    zv[i] = c < dc ? __ldg(z + o) : 0.f;
+                    gz[i] = (c < dc && g_zq) ? __ldg(g_zq + o) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = c0 + ty + 8 * i;
+                    if (c < dc) {
+                        const float e = tile[c][tx];
+                        const float t = __fmul_rn(__fmul_rn(norm, __fsub_rn(zv[i], e)), gv);
+                        dz_out[off + (int64_t)(d0 + c) * HW] = __fadd_rn(gz[i], t);
+                        tile[c][tx] = __fmul_rn(__fmul_rn(norm, __fsub_rn(e, zv[i])), gbeta);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (dE != nullptr) {
+            // half-warp per token: 16 lanes x float4 = 64 channels of one codebook-gradient row
+            const int l16 = lane & 15, half = lane >> 4;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int t = warp * 4 + i * 2 + half;
+                if (tt.off[t] >= 0) {
+                    float* drow = dE + (size_t)tt.code[t] * D + d0;
+                    for (int c = 4 * l16; c < dc; c += 64)
+                        red_add_v4(drow + c, tile[c + 0][t], tile[c + 1][t], tile[c + 2][t], tile[c + 3][t]);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // get_codebook_entry
 // ---------------------------------------------------------------------------
 template <bool kVec4>
@@ -421,6 +588,14 @@ extern "C" int vqb_gather_loss_st_f32(const float* z, const float* E, const int6
     }
     const dim3 block(sh.tx, sh.slices);
     double* parts = static_cast<double*>(partials);
+    if (D % 64 == 0) {
+        const int64_t tb = (N + kTileTok - 1) / kTileTok;
+        gather_loss_st_tiled_kernel<<<(unsigned)tb, 256, 0, s>>>(z, E, idx, N, D, HW, K, zq_out, parts, err_flag);
+        VQB_LAUNCH_CHECK("gather_loss_st_tiled_kernel");
+        loss_finalize_kernel<<<1, 256, 0, s>>>(parts, tb, 1.0 / ((double)N * D), beta, loss_out);
+        VQB_LAUNCH_CHECK("loss_finalize_kernel");
+        return VQB_OK;
+    }
     if (vec4_ok(D, E))
         gather_loss_st_kernel<true><<<(unsigned)blocks, block, 0, s>>>(
             z, E, idx, N, D, HW, K, sh.dims_per_slice, zq_out, parts, err_flag);
@@ -451,6 +626,13 @@ extern "C" int vqb_backward_f32(const float* z, const float* E, const int64_t* i
     const float norm = (float)(2.0 / ((double)N * D));
     unsigned long long* hist = reinterpret_cast<unsigned long long*>(hist_accum);
     const bool v4 = vec4_ok(D, E) && (!dE_accum || (reinterpret_cast<uintptr_t>(dE_accum) & 15u) == 0);
+    if (D % 64 == 0 && (!dE_accum || (reinterpret_cast<uintptr_t>(dE_accum) & 15u) == 0)) {
+        const int64_t tb = (N + kTileTok - 1) / kTileTok;
+        backward_tiled_kernel<<<(unsigned)tb, 256, 0, s>>>(z, E, idx, g_zq, g_vq, beta, norm, N, D, HW, K, dz_out,
+                                                           dE_accum, hist);
+        VQB_LAUNCH_CHECK("backward_tiled_kernel");
+        return VQB_OK;
+    }
     if (v4)
         backward_kernel<true><<<(unsigned)blocks, block, 0, s>>>(
             z, E, idx, g_zq, g_vq, beta, norm, N, D, HW, K, sh.dims_per_slice, dz_out, dE_accum, hist);

@@ -6,6 +6,8 @@
 //   mode 1  FFMA2 + FMNMX3 (the shipped mix)
 //   mode 2  scalar FFMA chains only
 //   mode 3  scalar FFMA + FMNMX3
+//   mode 4  FFMA2 + two 2-input FMNMX
+//   mode 5  FFMA2 + FMNMX3 applied one code pair late (software-pipelined minimum)
 // flops reported = 2 * 4 dims * tokens * codes (the algorithmic count of the search).
 #include "vqb_common.cuh"
 
@@ -41,7 +43,30 @@ __global__ void __launch_bounds__(256, 2) ubench_kernel(int sweeps, const float*
             const ulonglong2 v0 = *reinterpret_cast<const ulonglong2*>(tile + p * 8);
             const ulonglong2 v1 = *reinterpret_cast<const ulonglong2*>(tile + p * 8 + 4);
             const unsigned long long h2 = *reinterpret_cast<const unsigned long long*>(hbuf + 2 * p);
-            if constexpr (MODE == 0 || MODE == 1) {
+            if constexpr (MODE == 4) {
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    unsigned long long a = fma_f32x2(nz[t][0], v0.x, h2);
+                    a = fma_f32x2(nz[t][1], v0.y, a);
+                    a = fma_f32x2(nz[t][2], v1.x, a);
+                    a = fma_f32x2(nz[t][3], v1.y, a);
+                    float x, y;
+                    unpack_f32x2(a, x, y);
+                    m[t] = fminf(m[t], fminf(x, y));
+                }
+            } else if constexpr (MODE == 5) {
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    float x, y;
+                    unpack_f32x2(acc2[t], x, y);  // previous pair's scores
+                    unsigned long long a = fma_f32x2(nz[t][0], v0.x, h2);
+                    a = fma_f32x2(nz[t][1], v0.y, a);
+                    m[t] = min3_f32(m[t], x, y);
+                    a = fma_f32x2(nz[t][2], v1.x, a);
+                    a = fma_f32x2(nz[t][3], v1.y, a);
+                    acc2[t] = a;
+                }
+            } else if constexpr (MODE == 0 || MODE == 1) {
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
                     unsigned long long a = fma_f32x2(nz[t][0], v0.x, MODE == 1 ? h2 : acc2[t]);
@@ -98,7 +123,7 @@ using namespace vqb;
 
 extern "C" int vqb_ubench_launch(int mode, int sweeps, const float* src, float* sink, double* flops_host,
                                  vqb_stream_t stream) {
-    if (mode < 0 || mode > 3 || sweeps <= 0 || !src || !sink) {
+    if (mode < 0 || mode > 5 || sweeps <= 0 || !src || !sink) {
         set_error("vqb_ubench_launch: invalid argument");
         return VQB_ERR_INVALID_ARG;
     }
@@ -109,7 +134,9 @@ extern "C" int vqb_ubench_launch(int mode, int sweeps, const float* src, float* 
         case 0: ubench_kernel<0, T><<<blocks, 256, 0, s>>>(sweeps, src, sink); break;
         case 1: ubench_kernel<1, T><<<blocks, 256, 0, s>>>(sweeps, src, sink); break;
         case 2: ubench_kernel<2, T><<<blocks, 256, 0, s>>>(sweeps, src, sink); break;
-        default: ubench_kernel<3, T><<<blocks, 256, 0, s>>>(sweeps, src, sink); break;
+        case 3: ubench_kernel<3, T><<<blocks, 256, 0, s>>>(sweeps, src, sink); break;
+        case 4: ubench_kernel<4, T><<<blocks, 256, 0, s>>>(sweeps, src, sink); break;
+        default: ubench_kernel<5, T><<<blocks, 256, 0, s>>>(sweeps, src, sink); break;
     }
     VQB_LAUNCH_CHECK("ubench_kernel");
     if (flops_host) *flops_host = 2.0 * 4 * (double)blocks * 256 * T * kUbCodes * sweeps;
