@@ -42,6 +42,7 @@ extern "C" {
 #define VQB_ALGO_LOWD_FMA 1   /* D <= 16: packed-FFMA2 CUDA-core kernel         */
 #define VQB_ALGO_FP32_TILE 2  /* any D: fp32 register-tiled CUDA-core kernel    */
 #define VQB_ALGO_TCGEN05 3    /* D in {64,128,192,256}: bf16x3 tcgen05/TMEM     */
+#define VQB_ALGO_TCGEN05_F16 4 /* same D: one fp16 tcgen05 pass + exact fp32 re-score of the top-2 */
 
 typedef void* vqb_stream_t; /* a cudaStream_t */
 
@@ -58,7 +59,8 @@ VQB_API const char* vqb_last_error(void);
 VQB_API int vqb_device_query(int device, int* sm_count, int* cc_major, int* cc_minor,
                      size_t* smem_optin_bytes);
 
-/* launch-shape tuning knobs for experiments ("lowd_variant" = 0..4); defaults are the shipped ones */
+/* launch-shape tuning knobs for experiments ("lowd_variant" = 0..4, "tc16_cluster" = 1|2|4);
+ * defaults are the shipped ones */
 VQB_API int vqb_tune(const char* key, int value);
 
 /* ---- codebook pre-pass -------------------------------------------------
@@ -75,8 +77,9 @@ VQB_API int vqb_codebook_prepare_f32(const float* E, int K, int D, void* pack, s
  * materialising [N, K].  Minimises 0.5|e|^2 - z.e (|z|^2 is constant per row),
  * lowest index on ties, NaN rows -> the first NaN code like ATen's argmin.
  * idx_out[N] int64; dmin_out[N] (nullable) receives min_k(0.5|e_k|^2 - z.e_k).
- * stats_out (nullable, int64[4]): [0] tokens re-scored in fp32 by the tensor
- * path, [1] algorithm actually used, [2..3] reserved. */
+ * stats_out (nullable, int64[4]): [0] tokens fully re-scored in fp32 by a tensor
+ * path, [1] algorithm actually used, [2] tokens whose two candidates were
+ * re-scored (algo 4), [3] reserved. */
 VQB_API size_t vqb_search_workspace_bytes(int64_t B, int D, int64_t HW, int K, int algo);
 VQB_API int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                    const void* pack, int64_t* idx_out, float* dmin_out, void* workspace,

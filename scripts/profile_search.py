@@ -15,9 +15,11 @@ ap.add_argument("--codes", type=int, default=16384)
 ap.add_argument("--algo", type=int, default=0)
 ap.add_argument("--iters", type=int, default=4)
 ap.add_argument("--variant", type=int, default=0)
+ap.add_argument("--cluster", type=int, default=2)
 a = ap.parse_args()
 from vq_gan_b200 import _cabi
 _cabi.check(_cabi.lib().vqb_tune(b"lowd_variant", a.variant), "vqb_tune")
+_cabi.check(_cabi.lib().vqb_tune(b"tc16_cluster", a.cluster), "vqb_tune")
 B = a.tokens // 1024
 z = torch.randn(B, a.dim, 32, 32, device="cuda")
 E = torch.randn(a.codes, a.dim, device="cuda")
@@ -28,5 +30,5 @@ for _ in range(a.iters):
     torch.cuda.synchronize()
     (s, e), = ops.PROFILE
     ms = s.elapsed_time(e)
-    print(f"variant={a.variant} search algo={st.tolist()[1]} tokens={B * 1024} D={a.dim} K={a.codes}: {ms:.3f} ms "
+    print(f"variant={a.variant} cluster={a.cluster} search algo={st.tolist()[1]} tokens={B * 1024} D={a.dim} K={a.codes}: {ms:.3f} ms "
           f"{2.0 * B * 1024 * a.codes * a.dim / ms / 1e9:.2f} TFLOP/s algorithmic, rescored={st.tolist()[0]}")

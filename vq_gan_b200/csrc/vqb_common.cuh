@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
@@ -32,10 +33,12 @@ int sm_count();  // cached per current device
 
 // ---- packed codebook layout ----------------------------------------------
 // header (int32[64]): [0] first NaN code (K if none) [1] K [2] D [4] float bits of max 0.5|e|^2
+//                      [5] fp16 scale exponent se (e16 = fp16(E * 2^se)) [6] float bits of max|E| [7] bits of max |e - fp16(e)|
 // half_norm: float[Kpad]  0.5|e_k|^2, +inf for k >= K.  Read as consecutive
 //            (h[2p], h[2p+1]) pairs by the low-D kernel.
 // pairs    : float[Kpad/2][2D]  (D <= 16)  e_d(2p), e_d(2p+1) interleaved per d
 // ehi, elo : bf16[Kpad][D]      (tensor path) E ~= ehi + elo, zero rows for k >= K
+// e16      : fp16[Kpad][D]      (single-pass tensor path) fp16(E * 2^se), zero rows for k >= K
 constexpr int kPadCodes = 256;
 constexpr int kHeaderBytes = 256;
 constexpr int kLowDMax = 16;
@@ -51,7 +54,7 @@ __host__ __device__ inline bool tc_eligible_dim(int D) {
 
 struct PackLayout {
     int K, D, Kpad;
-    size_t off_half_norm, off_pairs, off_ehi, off_elo, total;
+    size_t off_half_norm, off_pairs, off_ehi, off_elo, off_e16, off_half_norm_fin, total;
     bool has_pairs, has_bf16;
 };
 
@@ -71,6 +74,10 @@ __host__ __device__ inline PackLayout pack_layout(int K, int D) {
     if (L.has_bf16) off = round_up_z(off + 2 * (size_t)L.Kpad * D, 1024);
     L.off_elo = off;
     if (L.has_bf16) off = round_up_z(off + 2 * (size_t)L.Kpad * D, 1024);
+    L.off_e16 = off;
+    if (L.has_bf16) off = round_up_z(off + 2 * (size_t)L.Kpad * D, 1024);
+    L.off_half_norm_fin = off;  // half norms with a large FINITE pad (1e38) for the key-packing epilogue
+    if (L.has_bf16) off = round_up_z(off + sizeof(float) * L.Kpad, 1024);
     L.total = off;
     return L;
 }
@@ -117,6 +124,11 @@ size_t search_tc_workspace_bytes(int64_t n_tokens, int D, int K);
 int launch_search_tc(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                      const void* pack, int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes,
                      int64_t* stats_out, cudaStream_t s);
+size_t search_tc16_workspace_bytes(int64_t n_tokens, int D, int K);
+int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
+                       const void* pack, int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes,
+                       int64_t* stats_out, cudaStream_t s);
 void set_lowd_variant(int v);
+void set_tc16_cluster(int c);
 
 }  // namespace vqb

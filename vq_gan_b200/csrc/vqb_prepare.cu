@@ -12,7 +12,29 @@ __global__ void prepare_header_kernel(int* header, int K, int D) {
         header[1] = K;
         header[2] = D;
         header[4] = 0;  // bits of max_k 0.5|e_k|^2 (atomicMax below; non-negative floats order as ints)
+        header[5] = 0;  // fp16 scale exponent, written by codebook_prepare_kernel
+        header[6] = 0;  // bits of max |E| (codebook_absmax_kernel)
+        header[7] = 0;  // bits of max_k |e_k - fp16 image of e_k| (residual of the single-pass tensor path)
     }
+}
+
+__global__ void __launch_bounds__(256) codebook_absmax_kernel(const float* __restrict__ E, size_t n, int* header) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = fabsf(E[i]);
+        if (v == v && v < INFINITY) m = fmaxf(m, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(&header[6], __float_as_int(m));
+}
+
+// power-of-two scale that puts max|E| into [512, 1024): keeps small entries out of the fp16
+// subnormal range and far from overflow; exact (no rounding) because it is a power of two
+__device__ __forceinline__ int fp16_scale_exponent(float maxabs) {
+    if (!(maxabs > 0.f) || maxabs == INFINITY) return 0;
+    int e = 9 - ilogbf(maxabs);
+    return e < -100 ? -100 : (e > 100 ? 100 : e);
 }
 
 // one warp per code row (padded rows included)
@@ -28,9 +50,12 @@ __global__ void __launch_bounds__(256) codebook_prepare_kernel(const float* __re
     float* pairs = reinterpret_cast<float*>(pack + L.off_pairs);
     __nv_bfloat16* ehi = reinterpret_cast<__nv_bfloat16*>(pack + L.off_ehi);
     __nv_bfloat16* elo = reinterpret_cast<__nv_bfloat16*>(pack + L.off_elo);
+    __half* e16 = reinterpret_cast<__half*>(pack + L.off_e16);
     const bool live = k < K;
+    const int se = fp16_scale_exponent(__int_as_float(header[6]));
+    if (k == 0 && lane == 0) header[5] = se;
 
-    float sq = 0.f;
+    float sq = 0.f, res = 0.f;
     bool bad = false;
     for (int d = lane; d < D; d += 32) {
         const float v = live ? E[(size_t)k * D + d] : 0.f;
@@ -45,15 +70,26 @@ __global__ void __launch_bounds__(256) codebook_prepare_kernel(const float* __re
             const float rem = v - __bfloat162float(hi);
             ehi[(size_t)k * D + d] = hi;
             elo[(size_t)k * D + d] = __float2bfloat16_rn(rem);
+            const __half hv = __float2half_rn(ldexpf(v, se));
+            e16[(size_t)k * D + d] = hv;
+            const float dv = v - ldexpf(__half2float(hv), -se);
+            res = fmaf(dv, dv, res);
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
         half_norm[k] = live ? 0.5f * sq : INFINITY;
+        if (L.has_bf16) {
+            const float h = 0.5f * sq;
+            reinterpret_cast<float*>(pack + L.off_half_norm_fin)[k] = (live && h < 1e38f) ? h : 1e38f;
+        }
         if (live && (bad || sq != sq)) atomicMin(&header[0], k);
         if (live && sq == sq) atomicMax(&header[4], __float_as_int(0.5f * sq));
+        if (live && res == res && res > 0.f) atomicMax(&header[7], __float_as_int(sqrtf(res)));
     }
 }
 
@@ -61,6 +97,13 @@ int launch_codebook_prepare(const float* E, int K, int D, void* pack, cudaStream
     const PackLayout L = pack_layout(K, D);
     prepare_header_kernel<<<1, 32, 0, s>>>(reinterpret_cast<int*>(pack), K, D);
     VQB_LAUNCH_CHECK("prepare_header_kernel");
+    if (L.has_bf16) {
+        const size_t n = (size_t)K * D;
+        size_t ab = (n + 255) / 256;
+        if (ab > (size_t)sm_count() * 8) ab = (size_t)sm_count() * 8;
+        codebook_absmax_kernel<<<(unsigned)ab, 256, 0, s>>>(E, n, reinterpret_cast<int*>(pack));
+        VQB_LAUNCH_CHECK("codebook_absmax_kernel");
+    }
     const int warps = 8;
     const int blocks = (L.Kpad + warps - 1) / warps;
     codebook_prepare_kernel<<<blocks, warps * 32, 0, s>>>(E, K, D, static_cast<unsigned char*>(pack), L);

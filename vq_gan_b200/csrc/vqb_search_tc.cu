@@ -16,100 +16,9 @@
 //                           being computed; running (min1, idx1, min2) per token row
 // Tokens whose top-2 gap is within the proven bf16x3 error bound are appended to
 // a list and re-scored exactly by the fp32 tile kernel (vqb_search_fp32.cu).
-#include <cuda.h>
-
-#include "vqb_common.cuh"
+#include "vqb_tc_common.cuh"
 
 namespace vqb {
-
-constexpr int kTcBM = 128;
-constexpr int kTcBN = 256;
-constexpr int kTcBK = 64;
-constexpr int kTcThreads = 256;
-constexpr int kTcABlockBytes = kTcBM * kTcBK * 2;  // 16 KB
-constexpr int kTcBStageBytes = kTcBN * kTcBK * 2;  // 32 KB
-constexpr int kTcSmemBudget = 227 * 1024;
-constexpr int kTcBarrierBytes = 256;
-
-__host__ __device__ constexpr int tc_stages(int nkb) {
-    // A (hi+lo) is resident: 2*nkb*16 KB; the rest holds B stages (1 KB lost to alignment)
-    int s = (kTcSmemBudget - 1024 - kTcBarrierBytes - 2 * nkb * kTcABlockBytes) / kTcBStageBytes;
-    return s > 6 ? 6 : s;
-}
-
-// ---- PTX wrappers ----------------------------------------------------------
-__device__ __forceinline__ uint32_t s32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void tc_mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tc_mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(s32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            s32(dst)),
-        "l"(map), "r"(s32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// K-major, 128B-swizzled operand tile: rows 128 B apart, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);       // start address
-    d |= (uint64_t)1 << 16;                           // leading byte offset (unused for SW128 K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset
-    d |= (uint64_t)1 << 46;                           // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
-    return d;
-}
-constexpr uint32_t kTcIdesc = (1u << 4)               // accumulator f32
-                              | (1u << 7) | (1u << 10)  // A, B = bf16 (K-major both)
-                              | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // ---------------------------------------------------------------------------
 // pre-pass: z[B, D, HW] fp32 -> zh, zl [N, D] bf16 (token-major) and |z_i|
@@ -406,6 +315,13 @@ __global__ void __launch_bounds__(256)
     dmin_out[tok] = (d != d) ? INFINITY : d;  // all-NaN rows report +inf like the fp32 kernel
 }
 
+int launch_exact_score(const float* z, const float* E, const float* half_norm, const int64_t* idx, int64_t N, int D,
+                       int64_t HW, int K, float* dmin_out, cudaStream_t s) {
+    exact_score_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(z, E, half_norm, idx, N, D, HW, K, dmin_out);
+    VQB_LAUNCH_CHECK("exact_score_kernel");
+    return VQB_OK;
+}
+
 __global__ void tc_stats_kernel(int64_t* stats, const int32_t* count) {
     stats[0] = *count;
     stats[1] = VQB_ALGO_TCGEN05;
@@ -461,8 +377,8 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// rows x D bf16 row-major, box = 64 columns x box_rows, 128B swizzle
-static int make_map(CUtensorMap* map, const void* base, uint64_t rows, int D, uint32_t box_rows) {
+// rows x D 16-bit row-major, box = 64 columns x box_rows, 128B swizzle
+int make_tc_map(CUtensorMap* map, const void* base, uint64_t rows, int D, uint32_t box_rows, bool fp16) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is unavailable in this driver");
@@ -472,7 +388,7 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t rows, int D, ui
     cuuint64_t strides[1] = {(cuuint64_t)D * 2};
     cuuint32_t box[2] = {(cuuint32_t)kTcBK, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -522,10 +438,10 @@ int launch_search_tc(const float* z, int64_t B, int D, int64_t HW, const float* 
     VQB_LAUNCH_CHECK("split_tokens_kernel");
 
     CUtensorMap mzh, mzl, meh, mel;
-    if (int rc = make_map(&mzh, zh, (uint64_t)N, D, kTcBM)) return rc;
-    if (int rc = make_map(&mzl, zl, (uint64_t)N, D, kTcBM)) return rc;
-    if (int rc = make_map(&meh, pk + L.off_ehi, (uint64_t)L.Kpad, D, kTcBN)) return rc;
-    if (int rc = make_map(&mel, pk + L.off_elo, (uint64_t)L.Kpad, D, kTcBN)) return rc;
+    if (int rc = make_tc_map(&mzh, zh, (uint64_t)N, D, kTcBM, false)) return rc;
+    if (int rc = make_tc_map(&mzl, zl, (uint64_t)N, D, kTcBM, false)) return rc;
+    if (int rc = make_tc_map(&meh, pk + L.off_ehi, (uint64_t)L.Kpad, D, kTcBN, false)) return rc;
+    if (int rc = make_tc_map(&mel, pk + L.off_elo, (uint64_t)L.Kpad, D, kTcBN, false)) return rc;
 
     TcParams p;
     p.N = N;

@@ -1,0 +1,697 @@
+// Single-pass fp16 tensor-core search with exact candidate re-scoring, D in {64,128,192,256}.
+// Replaces quantizer.py:68-76 of the reference; same contract as the fp32 kernel, one third of
+// the tensor work of the bf16x3 kernel (vqb_search_tc.cu).
+//
+//   approx[i,k] = 0.5|e_k|^2 - (zs_i . es_k) / (s_i * se),  zs = fp16(z_i * s_i), es = fp16(e_k * se)
+//   s_i, se powers of two (exact scaling).  With dz_i = z_i - zs_i/s_i, de_k = e_k - es_k/se:
+//   |approx - exact| <= eps_i = |dz_i| max|e| + (|z_i| + |dz_i|) max|de|  (Cauchy-Schwarz on the
+//   ACTUAL rounding residuals, measured by the pre-passes) + fp32 accumulation and key-mask terms.
+//
+// The epilogue works on groups of 4 consecutive codes: two FMNMX give the group minimum, the
+// group id rides in the low 8 mantissa bits, and a 7-FMNMX sorted insert keeps the four smallest
+// group minima per token -- 2.5 ALU ops per score, so the epilogue hides behind the MMAs.  Then,
+// with tau = 2 eps (any code whose exact score beats the approximate winner lies within tau):
+//   m2 - m1 > tau   -> every candidate is in group g1: its 4 codes are re-scored in fp32
+//   m3 - m1 > tau   -> candidates are in g1, g2: 8 codes;   m4 - m1 > tau -> g1..g3: 12 codes
+//   otherwise (or NaN) -> full fp32 re-score of the token (vqb_search_fp32.cu)
+//
+// Pipeline: persistent CTA per SM, 128-token tiles; warp 0 TMA producer (A = fp16 token tile,
+// resident; B = 256-code x 64-dim blocks through a ring of 32 KB stages), warp 1 MMA issuer
+// (tcgen05.mma kind::f16, 128x256x16, two 256-column TMEM accumulators), warp 2 TMEM allocator,
+// warps 4-11 epilogue (two warpgroups, 128 columns each).
+#include "vqb_tc_common.cuh"
+
+namespace vqb {
+
+constexpr int kT16Threads = 384;
+constexpr int kT16EpiThreads = 256;
+
+__host__ __device__ constexpr int tc16_stages(int nkb) {
+    int s = (kTcSmemBudget - 1024 - kTcBarrierBytes - 12288 - nkb * kTcABlockBytes) / kTcBStageBytes;
+    return s > 6 ? 6 : s;
+}
+
+constexpr uint32_t kT16Idesc = (1u << 4)  // accumulator f32; A, B = f16 (format 0), K-major
+                               | ((uint32_t)(kTcBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+
+// ---------------------------------------------------------------------------
+// pre-pass: z[B, D, HW] fp32 -> z16[N, D] fp16 scaled per token, 1/(s_i*se), |z_i|, |dz_i|
+// (one global read: the 32-token x D tile waits in shared memory while the scale is found)
+// ---------------------------------------------------------------------------
+constexpr int kSplitDimMax = 256;
+
+__global__ void __launch_bounds__(256)
+    split16_tokens_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW, const int* __restrict__ header,
+                          __half* __restrict__ z16, float* __restrict__ inv_scale, float* __restrict__ znorm,
+                          float* __restrict__ zres) {
+    __shared__ float tile[kSplitDimMax][33];
+    __shared__ float part_a[8][32];
+    __shared__ float part_b[8][32];
+    __shared__ int tok_exp[32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int64_t tok = t0 + tx;
+    const bool ok = tok < N;
+    int64_t off = 0;
+    if (ok) {
+        const int64_t b = tok / HW;
+        off = (b * D) * HW + (tok - b * HW);
+    }
+    // pass 1: stage the tile, per-token max |z| and sum of squares
+    float sq = 0.f, mx = 0.f;
+    bool finite = true;
+    for (int d = ty; d < D; d += 8) {
+        const float v = ok ? __ldg(z + off + (int64_t)d * HW) : 0.f;
+        tile[d][tx] = v;
+        sq = fmaf(v, v, sq);
+        const float a = fabsf(v);
+        finite &= (a < INFINITY);  // false for NaN as well
+        mx = fmaxf(mx, a);
+    }
+    part_a[ty][tx] = sq;
+    part_b[ty][tx] = finite ? mx : INFINITY;
+    __syncthreads();
+    if (ty == 0) {
+        float s = 0.f, m = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s += part_a[i][tx];
+            m = fmaxf(m, part_b[i][tx]);
+        }
+        int e = 0;
+        if (m > 0.f && m < INFINITY) {
+            e = 9 - ilogbf(m);  // max |z_i| * 2^e in [512, 1024)
+            e = e < -100 ? -100 : (e > 100 ? 100 : e);
+        }
+        tok_exp[tx] = e;
+        if (ok) {
+            znorm[tok] = sqrtf(s);
+            // a token with a NaN / inf coordinate gets a NaN scale: every approximate score becomes
+            // NaN and the token is re-scored by the fp32 kernel, which implements ATen's NaN rules
+            inv_scale[tok] = (m < INFINITY) ? ldexpf(1.f, -(e + header[5])) : __int_as_float(0x7fc00000);
+        }
+    }
+    __syncthreads();
+    // pass 2: scale, convert, write token-major rows; accumulate the rounding residual
+    float res = 0.f;
+    for (int i = 0; i < 4; ++i) {
+        const int r = ty + 8 * i;  // token within the block
+        const int64_t t = t0 + r;
+        const int ex = tok_exp[r];
+        const float back = ldexpf(1.f, -ex);
+        for (int d = 2 * tx; d < D; d += 64) {
+            const float a = tile[d][r], b2 = tile[d + 1][r];
+            const __half2 h = __floats2half2_rn(ldexpf(a, ex), ldexpf(b2, ex));
+            const float2 f = __half22float2(h);
+            const float da = a - f.x * back, db = b2 - f.y * back;
+            res = fmaf(da, da, res);
+            res = fmaf(db, db, res);
+            if (t < N) *reinterpret_cast<__half2*>(z16 + (size_t)t * D + d) = h;
+        }
+        // the 32 lanes of this warp hold the residual of token r: reduce and store
+        float tot = res;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (tx == 0 && t < N) zres[t] = sqrtf(tot);
+        res = 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------
+struct T16Params {
+    int64_t N;
+    int K, Kpad;
+    const float* half_norm;      // exact, +inf padded (re-score kernels)
+    const float* half_norm_fin;  // finite padding (epilogue keys must never be NaN)
+    const int* header;
+    const float* znorm;
+    const float* zres;       // |z_i - fp16 image of z_i|
+    const float* inv_scale;
+    int32_t* group1;         // [N] best group (code / 4)
+    int32_t* group2;         // [N] second group, or -1 when group1 alone holds every candidate
+    int32_t* group3;         // [N] third group, or -1
+    int32_t* pair_count;     // statistics only
+    int32_t* full_list;      // tokens needing a full fp32 re-score
+    int32_t* full_count;
+};
+
+// four smallest group minima of a token and the groups of the best three
+struct Top4 {
+    float v1, v2, v3, v4;
+    int i1, i2, i3;
+};
+
+// (value, index) lexicographic insert: equal keys from different tiles keep the lower index first
+__device__ __forceinline__ void top4_insert(Top4& g, float v, int i) {
+    if (v < g.v1 || (v == g.v1 && i < g.i1)) {
+        g.v4 = g.v3;
+        g.v3 = g.v2;
+        g.i3 = g.i2;
+        g.v2 = g.v1;
+        g.i2 = g.i1;
+        g.v1 = v;
+        g.i1 = i;
+    } else if (v < g.v2 || (v == g.v2 && i < g.i2)) {
+        g.v4 = g.v3;
+        g.v3 = g.v2;
+        g.i3 = g.i2;
+        g.v2 = v;
+        g.i2 = i;
+    } else if (v < g.v3 || (v == g.v3 && i < g.i3)) {
+        g.v4 = g.v3;
+        g.v3 = v;
+        g.i3 = i;
+    } else if (v < g.v4) {
+        g.v4 = v;
+    }
+}
+
+// CL = thread-block cluster size (1, 2 or 4).  With CL > 1 the CTAs of a cluster work on different
+// token tiles but sweep the codebook in lockstep: each CTA fetches 1/CL of every B stage and TMA
+// multicasts it to all of them, so the L2 -> SM operand traffic (the limiter of the single-pass
+// kernel: 32 KB of B per 512 tensor cycles per SM) drops by CL.
+template <int NKB, int CL>
+__global__ void __launch_bounds__(kT16Threads, 1)
+    search_tc16_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_e,
+                       T16Params p) {
+    constexpr int kStages = tc16_stages(NKB);
+    static_assert(kStages >= 2, "not enough shared memory for the B ring");
+    extern __shared__ unsigned char smem_unaligned[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) &
+                                                           ~(uintptr_t)1023);
+    unsigned char* a_tile = smem;
+    unsigned char* b_ring = smem + NKB * kTcABlockBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + kStages * kTcBStageBytes);
+    uint64_t* a_full = bars + 0;
+    uint64_t* a_empty = bars + 1;
+    uint64_t* tm_full = bars + 2;   // [2]
+    uint64_t* tm_empty = bars + 4;  // [2]
+    uint64_t* b_full = bars + 6;    // [kStages]
+    uint64_t* b_empty = bars + 6 + kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * kStages);
+    // hand-over of the upper-column warpgroup's top-4 to the lower one: 128 rows x 8 words (4 KB),
+    // then two 1024-float buffers of half norms for the current / next super-tile of 4 code tiles (8 KB)
+    float* xchg = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + kTcBarrierBytes);
+    float* hbuf = xchg + 128 * 8;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_m_tiles = (int)((p.N + kTcBM - 1) / kTcBM);
+    const int n_n_tiles = p.Kpad / kTcBN;
+    // every CTA of a cluster runs the same number of rounds (tiles past the end are all padding:
+    // TMA zero-fills them and the epilogue drops their rows)
+    const int n_rounds = (n_m_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
+
+    if (threadIdx.x == 0) {
+        tc_mbar_init(a_full, 1);
+        tc_mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc_mbar_init(tm_full + i, 1);
+            tc_mbar_init(tm_empty + i, kT16EpiThreads);
+        }
+        for (int i = 0; i < kStages; ++i) {
+            tc_mbar_init(b_full + i, 1);
+            tc_mbar_init(b_empty + i, CL);  // released by the MMA issuer of every CTA in the cluster
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();  // peers' barriers exist before anything remote touches them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, bphase = 0, aphase = 0;
+            for (int round = 0; round < n_rounds; ++round) {
+                const int mt = blockIdx.x + round * gridDim.x;
+                tc_mbar_wait(a_empty, aphase ^ 1);
+                tc_mbar_expect_tx(a_full, NKB * kTcABlockBytes);
+#pragma unroll
+                for (int kb = 0; kb < NKB; ++kb)
+                    tma_load_2d(a_tile + kb * kTcABlockBytes, &map_z, a_full, kb * kTcBK, mt * kTcBM);
+                aphase ^= 1;
+                for (int nt = 0; nt < n_n_tiles; ++nt) {
+                    for (int kb = 0; kb < NKB; ++kb) {
+                        tc_mbar_wait(b_empty + stage, bphase ^ 1);
+                        tc_mbar_expect_tx(b_full + stage, kTcBStageBytes);
+                        if constexpr (CL > 1) {
+                            constexpr int kRows = kTcBN / CL;  // this CTA's slice of the stage
+                            tma_load_2d_mc(b_ring + stage * kTcBStageBytes + cta_rank * (kTcBStageBytes / CL), &map_e,
+                                           b_full + stage, kb * kTcBK, nt * kTcBN + (int)cta_rank * kRows, kMask);
+                        } else {
+                            tma_load_2d(b_ring + stage * kTcBStageBytes, &map_e, b_full + stage, kb * kTcBK,
+                                        nt * kTcBN);
+                        }
+                        if (++stage == kStages) {
+                            stage = 0;
+                            bphase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, bphase = 0, aphase = 0, acc = 0, accphase = 0;
+            for (int round = 0; round < n_rounds; ++round) {
+                tc_mbar_wait(a_full, aphase);
+                aphase ^= 1;
+                tc_fence_after();
+                for (int nt = 0; nt < n_n_tiles; ++nt) {
+                    tc_mbar_wait(tm_empty + acc, accphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * kTcBN;
+                    for (int kb = 0; kb < NKB; ++kb) {
+                        const uint32_t as = s32(a_tile + kb * kTcABlockBytes);
+                        tc_mbar_wait(b_full + stage, bphase);
+                        tc_fence_after();
+                        const uint32_t bs = s32(b_ring + stage * kTcBStageBytes);
+#pragma unroll
+                        for (int k4 = 0; k4 < kTcBK / 16; ++k4)
+                            umma_bf16(d_tmem, umma_desc_sw128(as + k4 * 32), umma_desc_sw128(bs + k4 * 32), kT16Idesc,
+                                      (kb | k4) != 0);
+                        if constexpr (CL > 1)
+                            umma_commit_mc(b_empty + stage, kMask);
+                        else
+                            umma_commit(b_empty + stage);
+                        if (++stage == kStages) {
+                            stage = 0;
+                            bphase ^= 1;
+                        }
+                    }
+                    umma_commit(tm_full + acc);
+                    if (++acc == 2) {
+                        acc = 0;
+                        accphase ^= 1;
+                    }
+                }
+                umma_commit(a_empty);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (8 warps) =====================
+        const int q = warp & 3;           // TMEM lane quarter this warp may read
+        const int hsel = (warp - 4) >> 2;  // column half: 0 -> [0,128), 1 -> [128,256)
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const int first_nan = p.header[0];
+        const float h_max = __int_as_float(p.header[4]);
+        const float e_max = sqrtf(2.f * h_max);
+        const float de_max = __int_as_float(p.header[7]);  // max_k |e_k - fp16 image of e_k|
+        const int row_in_tile = q * 32 + lane;
+        const int epi_tid = threadIdx.x - 128;  // 0..255
+        const int n_super = (n_n_tiles + 3) / 4;
+        const uint32_t hbuf_addr = s32(hbuf);
+        uint32_t hsel_buf = 0;  // which half-norm buffer holds the current super-tile
+#pragma unroll
+        for (int j = 0; j < 4; ++j)  // super-tile 0
+            hbuf[j * kTcBN + epi_tid] = (j < n_n_tiles) ? __ldg(p.half_norm_fin + j * kTcBN + epi_tid) : 1e38f;
+        asm volatile("bar.sync 1, %0;" ::"n"(kT16EpiThreads) : "memory");
+        uint32_t acc = 0, accphase = 0;
+        for (int round = 0; round < n_rounds; ++round) {
+            const int mt = blockIdx.x + round * gridDim.x;
+            const int64_t row = (int64_t)mt * kTcBM + row_in_tile;
+            const float neg_inv = (row < p.N) ? -p.inv_scale[row] : 0.f;
+            Top4 g;
+            g.v1 = g.v2 = g.v3 = g.v4 = INFINITY;
+            g.i1 = g.i2 = g.i3 = 0;
+            // code tiles are processed in super-tiles of 4 (1024 codes = 256 groups): the group id
+            // within the super-tile rides in the low 8 mantissa bits, and the running top-4 is merged
+            // (and the half-norm buffer rotated, one barrier) once per super-tile
+            for (int st = 0; st < n_super; ++st) {
+                const int tiles_here = (n_n_tiles - st * 4) < 4 ? (n_n_tiles - st * 4) : 4;
+                // prefetch this thread's share of the NEXT super-tile's half norms
+                const int next_st = (st + 1 < n_super) ? st + 1 : 0;
+                float h_next[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = next_st * 4 + j;
+                    h_next[j] = (t < n_n_tiles) ? __ldg(p.half_norm_fin + t * kTcBN + epi_tid) : 1e38f;
+                }
+                float k1 = INFINITY, k2 = INFINITY, k3 = INFINITY, k4 = INFINITY;
+                const uint32_t hs_base = hbuf_addr + (hsel_buf & 1) * (4 * kTcBN * 4) + hsel * 128 * 4;
+#pragma unroll 1
+                for (int tj = 0; tj < tiles_here; ++tj) {
+                    tc_mbar_wait(tm_full + acc, accphase);
+                    tc_fence_after();
+                    const uint32_t t_acc = tmem_base + lane_addr + acc * kTcBN + hsel * 128;
+                    const uint32_t hs = hs_base + tj * (kTcBN * 4);
+                    const uint32_t id_base = (uint32_t)(tj * 64 + hsel * 32);
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32_issue(t_acc, ra);
+#pragma unroll
+                    for (int c0 = 0; c0 < 128; c0 += 32) {
+                        uint32_t(&r)[32] = ((c0 >> 5) & 1) ? rb : ra;
+                        uint32_t(&rn)[32] = ((c0 >> 5) & 1) ? ra : rb;
+                        tmem_ld_wait();
+                        if (c0 + 32 < 128) tmem_ld32_issue(t_acc + c0 + 32, rn);
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            float4 h4;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(h4.x), "=f"(h4.y), "=f"(h4.z), "=f"(h4.w)
+                                         : "r"(hs + (c0 + c4 * 4) * 4));
+                            const float s0 = fmaf(__uint_as_float(r[c4 * 4 + 0]), neg_inv, h4.x);
+                            const float s1 = fmaf(__uint_as_float(r[c4 * 4 + 1]), neg_inv, h4.y);
+                            const float s2 = fmaf(__uint_as_float(r[c4 * 4 + 2]), neg_inv, h4.z);
+                            const float s3 = fmaf(__uint_as_float(r[c4 * 4 + 3]), neg_inv, h4.w);
+                            const float gm = fminf(min3_f32(s0, s1, s2), s3);
+                            const uint32_t gid = id_base + (uint32_t)((c0 >> 2) + c4);
+                            const float key = __uint_as_float((__float_as_uint(gm) & 0xffffff00u) | gid);
+                            // sorted insert of key into (k1 <= k2 <= k3 <= k4)
+                            const float n2 = fminf(k2, fmaxf(k1, key));
+                            const float n3 = fminf(k3, fmaxf(k2, key));
+                            const float n4 = fminf(k4, fmaxf(k3, key));
+                            k1 = fminf(k1, key);
+                            k2 = n2;
+                            k3 = n3;
+                            k4 = n4;
+                        }
+                    }
+                    tc_fence_before();
+                    tc_mbar_arrive(tm_empty + acc);
+                    if (++acc == 2) {
+                        acc = 0;
+                        accphase ^= 1;
+                    }
+                }
+                // publish the next super-tile's half norms; the barrier also fences the buffer reuse
+                {
+                    float* nb = hbuf + ((hsel_buf + 1) & 1) * (4 * kTcBN);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) nb[j * kTcBN + epi_tid] = h_next[j];
+                }
+                ++hsel_buf;
+                asm volatile("bar.sync 1, %0;" ::"n"(kT16EpiThreads) : "memory");
+                // merge the super-tile's top-4 into the running top-4 (earlier codes win ties)
+                if (k1 < g.v4) {
+                    const int base = st * 256;
+                    top4_insert(g, k1, base + (int)(__float_as_uint(k1) & 0xffu));
+                    top4_insert(g, k2, base + (int)(__float_as_uint(k2) & 0xffu));
+                    top4_insert(g, k3, base + (int)(__float_as_uint(k3) & 0xffu));
+                    top4_insert(g, k4, base + (int)(__float_as_uint(k4) & 0xffu));
+                }
+            }
+            // ---- combine the two column halves of each row (named barrier over the epilogue warps)
+            if (hsel == 1) {
+                float* x = xchg + row_in_tile * 8;
+                x[0] = g.v1;
+                x[1] = g.v2;
+                x[2] = g.v3;
+                x[3] = g.v4;
+                x[4] = __int_as_float(g.i1);
+                x[5] = __int_as_float(g.i2);
+                x[6] = __int_as_float(g.i3);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kT16EpiThreads) : "memory");
+            if (hsel == 0 && row < p.N) {
+                const float* x = xchg + row_in_tile * 8;
+                Top4 m = g;
+                top4_insert(m, x[0], __float_as_int(x[4]));
+                top4_insert(m, x[1], __float_as_int(x[5]));
+                top4_insert(m, x[2], __float_as_int(x[6]));
+                if (x[3] < m.v4) m.v4 = x[3];
+                // eps_i: Cauchy-Schwarz on the measured fp16 residuals + fp32 accumulation (2^-15
+                // relative, covers both this kernel's and the re-score's sums) + the 8 masked bits
+                const float zn = p.znorm[row], zr = p.zres[row];
+                const float eps = zr * e_max + (zn + zr) * de_max + (1.f / 32768.f) * zn * e_max +
+                                  (1.f / 16384.f) * (h_max + zn * e_max);
+                const float tau = 2.f * eps;
+                const bool only1 = (m.v2 - m.v1) > tau;  // every candidate is in group 1
+                const bool only2 = (m.v3 - m.v1) > tau;  // ... in groups 1-2
+                const bool only3 = (m.v4 - m.v1) > tau;  // ... in groups 1-3
+                p.group1[row] = m.i1;
+                p.group2[row] = only1 ? -1 : m.i2;
+                p.group3[row] = only2 ? -1 : m.i3;
+                if (first_nan < p.K || !only3) {
+                    const int slot = atomicAdd(p.full_count, 1);
+                    p.full_list[slot] = (int32_t)row;
+                } else if (!only1) {
+                    atomicAdd(p.pair_count, 1);
+                }
+            }
+            // the hand-over buffer is reused by the next token tile
+            asm volatile("bar.sync 1, %0;" ::"n"(kT16EpiThreads) : "memory");
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// Exact fp32 re-score of the candidate groups of every token: the 4 codes of group1 and, when
+// present, those of group2 and group3.  A CTA stages 32 tokens x D of z in shared memory (coalesced),
+// then each warp takes 4 tokens; lanes run along the channels so the candidate rows (4 adjacent
+// codebook rows = one contiguous block) are read as full lines.  Lowest index wins ties.
+__global__ void __launch_bounds__(256)
+    rescore_groups_kernel(const float* __restrict__ z, const float* __restrict__ E, const float* __restrict__ half_norm,
+                          const int32_t* __restrict__ group1, const int32_t* __restrict__ group2,
+                          const int32_t* __restrict__ group3, int64_t N, int D, int64_t HW, int K,
+                          int64_t* __restrict__ idx_out, float* __restrict__ dmin_out) {
+    __shared__ float tile[kSplitDimMax][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    {
+        const int64_t tok = t0 + tx;
+        if (tok < N) {
+            const int64_t b = tok / HW;
+            const float* zp = z + (b * D) * HW + (tok - b * HW);
+            for (int d = ty; d < D; d += 8) tile[d][tx] = __ldg(zp + (int64_t)d * HW);
+        }
+    }
+    __syncthreads();
+    const int lane = tx, warp = ty;
+    for (int i = 0; i < 4; ++i) {
+        const int r = warp * 4 + i;
+        const int64_t tok = t0 + r;
+        if (tok >= N) break;  // warp-uniform
+        float best = INFINITY;
+        int best_k = 0x7fffffff;
+        const int first_k = group1[tok] * 4;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+            const int grp = pass == 0 ? group1[tok] : (pass == 1 ? group2[tok] : group3[tok]);
+            if (grp < 0) break;  // warp-uniform
+            const int k0 = grp * 4;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int d = lane; d < D; d += 32) {
+                const float zv = tile[d][r];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int k = k0 + c;
+                    const float e = (k < K) ? __ldg(E + (size_t)k * D + d) : 0.f;
+                    acc[c] = fmaf(zv, e, acc[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+                const int k = k0 + c;
+                if (k < K) {
+                    const float dsc = half_norm[k] - acc[c];
+                    // (score, index) lexicographic minimum; NaN scores never win
+                    if (dsc < best || (dsc == best && k < best_k)) {
+                        best = dsc;
+                        best_k = k;
+                    }
+                }
+            }
+        }
+        if (best_k == 0x7fffffff) best_k = first_k < K ? first_k : 0;
+        if (lane == 0) {
+            idx_out[tok] = best_k;
+            if (dmin_out) dmin_out[tok] = best;
+        }
+    }
+}
+
+__global__ void tc16_stats_kernel(int64_t* stats, const int32_t* full_count, const int32_t* pair_count) {
+    stats[0] = *full_count;
+    stats[1] = VQB_ALGO_TCGEN05_F16;
+    stats[2] = *pair_count;
+    stats[3] = 0;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct T16Workspace {
+    size_t off_z16, off_inv, off_znorm, off_zres, off_g1, off_g2, off_g3, off_full, off_counts, off_keys, keys_bytes, total;
+};
+
+static T16Workspace t16_workspace(int64_t N, int D) {
+    T16Workspace w;
+    size_t off = 0;
+    w.off_z16 = off;
+    off = round_up_z(off + 2 * (size_t)N * D, 1024);
+    w.off_inv = off;
+    off = round_up_z(off + 4 * (size_t)N, 1024);
+    w.off_znorm = off;
+    off = round_up_z(off + 4 * (size_t)N, 1024);
+    w.off_zres = off;
+    off = round_up_z(off + 4 * (size_t)N, 1024);
+    w.off_g1 = off;
+    off = round_up_z(off + 4 * (size_t)N, 1024);
+    w.off_g2 = off;
+    off = round_up_z(off + 4 * (size_t)N, 1024);
+    w.off_g3 = off;
+    off = round_up_z(off + 4 * (size_t)N, 1024);
+    w.off_full = off;
+    off = round_up_z(off + 4 * (size_t)N, 1024);
+    w.off_counts = off;
+    off += 1024;
+    w.off_keys = off;
+    w.keys_bytes = search_fp32_workspace_bytes(N);
+    off = round_up_z(off + w.keys_bytes, 1024);
+    w.total = off;
+    return w;
+}
+
+size_t search_tc16_workspace_bytes(int64_t n_tokens, int D, int K) {
+    (void)K;
+    return t16_workspace(n_tokens, D).total;
+}
+
+static int g_tc16_cluster = 2;
+void set_tc16_cluster(int c) { g_tc16_cluster = c; }
+
+template <int NKB, int CL>
+static int launch_tc16_cl(const CUtensorMap& mz, const CUtensorMap& me, const T16Params& p, cudaStream_t s) {
+    constexpr int kStages = tc16_stages(NKB);
+    const size_t smem = 1024 + NKB * kTcABlockBytes + (size_t)kStages * kTcBStageBytes + kTcBarrierBytes + 12288;
+    VQB_CUDA_TRY(cudaFuncSetAttribute(search_tc16_kernel<NKB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    const int n_m_tiles = (int)((p.N + kTcBM - 1) / kTcBM);
+    int grid = n_m_tiles < sm_count() ? n_m_tiles : sm_count();
+    grid = (grid + CL - 1) / CL * CL;               // whole clusters
+    if (grid > sm_count()) grid = sm_count() / CL * CL;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kT16Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (CL > 1) {
+        // persistent kernel: never launch more clusters than can be co-resident (GPC granularity
+        // strands some SMs for larger clusters)
+        int max_clusters = 0;
+        VQB_CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, search_tc16_kernel<NKB, CL>, &cfg));
+        if (max_clusters > 0 && grid > max_clusters * CL) {
+            grid = max_clusters * CL;
+            cfg.gridDim = dim3((unsigned)grid);
+        }
+    }
+    VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_tc16_kernel<NKB, CL>, mz, me, p));
+    return VQB_OK;
+}
+
+template <int NKB>
+static int launch_tc16_t(const CUtensorMap& mz, const CUtensorMap& me1, const CUtensorMap& me2, const CUtensorMap& me4,
+                         const T16Params& p, cudaStream_t s) {
+    switch (g_tc16_cluster) {
+        case 1: return launch_tc16_cl<NKB, 1>(mz, me1, p, s);
+        case 4: return launch_tc16_cl<NKB, 4>(mz, me4, p, s);
+        default: return launch_tc16_cl<NKB, 2>(mz, me2, p, s);
+    }
+}
+
+int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float* E, int K, const void* pack,
+                       int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes, int64_t* stats_out,
+                       cudaStream_t s) {
+    const int64_t N = B * HW;
+    const T16Workspace w = t16_workspace(N, D);
+    if (!ws || ws_bytes < w.total) {
+        set_error("fp16 tensor search workspace too small: %zu < %zu", ws_bytes, w.total);
+        return VQB_ERR_WORKSPACE;
+    }
+    if ((reinterpret_cast<uintptr_t>(ws) & 255u) != 0) {
+        set_error("fp16 tensor search workspace must be 256-byte aligned");
+        return VQB_ERR_INVALID_ARG;
+    }
+    const PackLayout L = pack_layout(K, D);
+    unsigned char* wsb = static_cast<unsigned char*>(ws);
+    const unsigned char* pk = static_cast<const unsigned char*>(pack);
+    __half* z16 = reinterpret_cast<__half*>(wsb + w.off_z16);
+    float* inv = reinterpret_cast<float*>(wsb + w.off_inv);
+    float* znorm = reinterpret_cast<float*>(wsb + w.off_znorm);
+    float* zres = reinterpret_cast<float*>(wsb + w.off_zres);
+    int32_t* counts = reinterpret_cast<int32_t*>(wsb + w.off_counts);
+
+    VQB_CUDA_TRY(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), s));
+    split16_tokens_kernel<<<(unsigned)((N + 31) / 32), 256, 0, s>>>(z, N, D, HW, reinterpret_cast<const int*>(pk), z16,
+                                                                   inv, znorm, zres);
+    VQB_LAUNCH_CHECK("split16_tokens_kernel");
+
+    // codebook maps: the box is the slice one CTA of the cluster fetches (256, 128 or 64 rows)
+    CUtensorMap mz, me1, me2, me4;
+    if (int rc = make_tc_map(&mz, z16, (uint64_t)N, D, kTcBM, true)) return rc;
+    if (int rc = make_tc_map(&me1, pk + L.off_e16, (uint64_t)L.Kpad, D, kTcBN, true)) return rc;
+    if (int rc = make_tc_map(&me2, pk + L.off_e16, (uint64_t)L.Kpad, D, kTcBN / 2, true)) return rc;
+    if (int rc = make_tc_map(&me4, pk + L.off_e16, (uint64_t)L.Kpad, D, kTcBN / 4, true)) return rc;
+
+    T16Params p;
+    p.N = N;
+    p.K = K;
+    p.Kpad = L.Kpad;
+    p.half_norm = reinterpret_cast<const float*>(pk + L.off_half_norm);
+    p.half_norm_fin = reinterpret_cast<const float*>(pk + L.off_half_norm_fin);
+    p.header = reinterpret_cast<const int*>(pk);
+    p.znorm = znorm;
+    p.zres = zres;
+    p.inv_scale = inv;
+    p.group1 = reinterpret_cast<int32_t*>(wsb + w.off_g1);
+    p.group2 = reinterpret_cast<int32_t*>(wsb + w.off_g2);
+    p.group3 = reinterpret_cast<int32_t*>(wsb + w.off_g3);
+    p.pair_count = counts + 1;
+    p.full_list = reinterpret_cast<int32_t*>(wsb + w.off_full);
+    p.full_count = counts + 0;
+    int rc;
+    switch (D / kTcBK) {
+        case 1: rc = launch_tc16_t<1>(mz, me1, me2, me4, p, s); break;
+        case 2: rc = launch_tc16_t<2>(mz, me1, me2, me4, p, s); break;
+        case 3: rc = launch_tc16_t<3>(mz, me1, me2, me4, p, s); break;
+        case 4: rc = launch_tc16_t<4>(mz, me1, me2, me4, p, s); break;
+        default:
+            set_error("fp16 tensor search supports D in {64,128,192,256}, got %d", D);
+            return VQB_ERR_UNSUPPORTED;
+    }
+    if (rc != VQB_OK) return rc;
+    // exact fp32 choice among the 4 (or 8) certified candidates of every token
+    rescore_groups_kernel<<<(unsigned)((N + 31) / 32), 256, 0, s>>>(z, E, p.half_norm, p.group1, p.group2, p.group3, N, D,
+                                                                    HW, K, idx_out, dmin_out);
+    VQB_LAUNCH_CHECK("rescore_groups_kernel");
+    // ambiguous tokens: full exact fp32 search
+    rc = launch_search_fp32(z, B, D, HW, E, K, pack, p.full_list, p.full_count, N, wsb + w.off_keys, w.keys_bytes,
+                            idx_out, dmin_out, s);
+    if (rc != VQB_OK) return rc;
+    if (stats_out) {
+        tc16_stats_kernel<<<1, 1, 0, s>>>(stats_out, p.full_count, p.pair_count);
+        VQB_LAUNCH_CHECK("tc16_stats_kernel");
+    }
+    return VQB_OK;
+}
+
+}  // namespace vqb

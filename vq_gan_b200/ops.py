@@ -37,7 +37,8 @@ def _search_kernels(D: int, algo: int) -> int:
         algo = (_cabi.ALGO_LOWD_FMA if D <= 16 else
                 _cabi.ALGO_TCGEN05 if (D % 64 == 0 and D <= 256) else _cabi.ALGO_FP32_TILE)
     # lowd: search + stats; fp32: search (+ finalize) + stats; tcgen05: split, mma, re-score, finalize, stats
-    return {_cabi.ALGO_LOWD_FMA: 2, _cabi.ALGO_FP32_TILE: 3, _cabi.ALGO_TCGEN05: 5}[algo]
+    return {_cabi.ALGO_LOWD_FMA: 2, _cabi.ALGO_FP32_TILE: 3, _cabi.ALGO_TCGEN05: 5,
+            _cabi.ALGO_TCGEN05_F16: 6}[algo]
 
 
 def _p(t: Optional[Tensor]):
