@@ -258,11 +258,11 @@ def run_sharded_encode(args, world, rank, local_rank, device, B, D, H, W, K, des
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"c5: {desc}", "tokens_per_gpu_per_step": tokens, "D": D, "K": K,
                        "codes_per_rank": khi - klo, "parallelism": f"codebook-sharded x{world}",
-                       "l2": "codebook shard (bf16 hi+lo) and 4 rotating latent sets exceed the 126 MB L2"},
-            "roofline": {"bound": "tensor", "kernel": "search_tc_kernel", "achieved": achieved,
+                       "l2": "4 rotating latent sets (235 MB) exceed the 126 MB L2"},
+            "roofline": {"bound": "tensor", "kernel": "search_tc16_kernel", "achieved": achieved,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_tflops_sustained"], "executed_flops_factor": 3,
-                         "frac_executed": 3 * achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "frac": achieved / peaks["bf16_tflops_sustained"], "executed_flops_factor": 1,
+                         "frac_executed": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
                          "kernel_ms": s_ms, "algorithmic_flops_per_launch": flops,
                          "step_share": s_ms * len(search_ms) / ms_total},
             "exchange_bytes_per_step": {"all_gather_latents": tokens * D * 4 * max(world - 1, 0),
@@ -417,9 +417,12 @@ def run_gpu_arm(args):
         algo = int(stats[1])
         flops = 2.0 * tokens * K * D
         s_ms = statistics.mean(search_ms) if search_ms else float("nan")
-        if algo == 3:
+        factor = {3: 3, 4: 1}.get(algo, 1)
+        if algo in (3, 4):
             bound, peak, unit = "tensor", peaks["bf16_tflops_sustained"], "TFLOP/s"
-            peak_note = f"cuBLAS bf16 sustained, {peaks['source']} (algorithmic flops; x3 executed for bf16x3)"
+            peak_note = (f"cuBLAS bf16 sustained, {peaks['source']} (algorithmic flops 2NKD; the kernel executes "
+                         f"x{factor}: " + ("bf16x3 split" if algo == 3 else "one fp16 pass, exact fp32 re-score "
+                                            "of the certified candidates") + ")")
         else:
             bound, peak, unit = "fma", fma_peak, "TFLOP/s"
             peak_note = ("FP32 FMA peak measured in this run by vqb_fma_peak_launch "
@@ -427,11 +430,11 @@ def run_gpu_arm(args):
                          "MEASURED_PEAKS.json has no FMA figure")
         achieved = flops / (s_ms * 1e-3) / 1e12
         roofline = {"bound": bound, "kernel": {1: "search_lowd_kernel", 2: "search_fp32_kernel",
-                                               3: "search_tc_kernel"}.get(algo, str(algo)),
+                                               3: "search_tc_kernel", 4: "search_tc16_kernel"}.get(algo, str(algo)),
                     "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                     "traffic": None, "kernel_ms": s_ms, "algorithmic_flops_per_launch": flops,
-                    "executed_flops_factor": 3 if algo == 3 else 1,
-                    "frac_executed": achieved * (3 if algo == 3 else 1) / peak,
+                    "executed_flops_factor": factor,
+                    "frac_executed": achieved * factor / peak,
                     "peak_source": peak_note,
                     "step_share": s_ms * len(search_ms) / ms_total if search_ms else None}
         # HBM-side kernels: algorithmic bytes per token 8D+8 (tail) and 12D+8 (+ dE once) (backward)
@@ -451,8 +454,10 @@ def run_gpu_arm(args):
             "config": {"workload": f"{args.workload}: {desc}", "tokens_per_gpu_per_step": tokens,
                        "D": D, "K": K, "beta": BETA, "parallelism": f"dp{world}",
                        "l2": f"{n_rot} rotating input sets ({n_rot * bytes_per_set / 1e6:.0f} MB) > 126 MB L2",
-                       "search_algo": {1: "lowd_fma", 2: "fp32_tile", 3: "tcgen05_bf16x3"}.get(algo, str(algo)),
-                       "rescored_tokens_last_step": int(stats[0])},
+                       "search_algo": {1: "lowd_fma", 2: "fp32_tile", 3: "tcgen05_bf16x3",
+                                       4: "tcgen05_f16_certified"}.get(algo, str(algo)),
+                       "rescored_tokens_last_step": int(stats[0]),
+                       "multi_group_tokens_last_step": int(stats[2])},
             "roofline": roofline,
             "e2e": {"value": tokens * world * e2e_steps / (e2e_ms * 1e-3), "unit": "tokens/s",
                     "h2d_bytes_per_step": zs[0].numel() * 4, "d2h_bytes_per_step": tokens * 8 + 8,

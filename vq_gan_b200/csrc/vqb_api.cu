@@ -101,7 +101,7 @@ extern "C" int vqb_codebook_prepare_f32(const float* E, int K, int D, void* pack
 static int resolve_algo(int algo, int D) {
     if (algo != VQB_ALGO_AUTO) return algo;
     if (D <= kLowDMax) return VQB_ALGO_LOWD_FMA;
-    if (tc_eligible_dim(D)) return VQB_ALGO_TCGEN05;
+    if (tc_eligible_dim(D)) return VQB_ALGO_TCGEN05_F16;  // single fp16 pass + exact re-score: 2.4x the bf16x3 kernel
     return VQB_ALGO_FP32_TILE;
 }
 

@@ -35,7 +35,7 @@ def _search_kernels(D: int, algo: int) -> int:
     """libvqb200 kernels one vqb_search_f32 call launches (mirrors resolve_algo in vqb_api.cu)."""
     if algo == _cabi.ALGO_AUTO:
         algo = (_cabi.ALGO_LOWD_FMA if D <= 16 else
-                _cabi.ALGO_TCGEN05 if (D % 64 == 0 and D <= 256) else _cabi.ALGO_FP32_TILE)
+                _cabi.ALGO_TCGEN05_F16 if (D % 64 == 0 and 64 <= D <= 256) else _cabi.ALGO_FP32_TILE)
     # lowd: search + stats; fp32: search (+ finalize) + stats; tcgen05: split, mma, re-score, finalize, stats
     return {_cabi.ALGO_LOWD_FMA: 2, _cabi.ALGO_FP32_TILE: 3, _cabi.ALGO_TCGEN05: 5,
             _cabi.ALGO_TCGEN05_F16: 6}[algo]
