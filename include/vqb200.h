@@ -43,6 +43,8 @@ extern "C" {
 #define VQB_ALGO_FP32_TILE 2  /* any D: fp32 register-tiled CUDA-core kernel    */
 #define VQB_ALGO_TCGEN05 3    /* D in {64,128,192,256}: bf16x3 tcgen05/TMEM     */
 #define VQB_ALGO_TCGEN05_F16 4 /* same D: one fp16 tcgen05 pass + exact fp32 re-score of the top-2 */
+#define VQB_ALGO_TCGEN05_TF32X3 5 /* D <= 16: tf32x3 tcgen05 pass, certified 32-code chunk re-scored
+                                     with the FMA chain of algo 1 (bit-identical indices) */
 
 typedef void* vqb_stream_t; /* a cudaStream_t */
 
@@ -59,7 +61,8 @@ VQB_API const char* vqb_last_error(void);
 VQB_API int vqb_device_query(int device, int* sm_count, int* cc_major, int* cc_minor,
                      size_t* smem_optin_bytes);
 
-/* launch-shape tuning knobs for experiments ("lowd_variant" = 0..4, "tc16_cluster" = 1|2|4);
+/* launch-shape tuning knobs for experiments ("lowd_variant" = 0..4, "tc16_cluster" and
+ * "tclow_cluster" = 1|2|4);
  * defaults are the shipped ones */
 VQB_API int vqb_tune(const char* key, int value);
 

@@ -26,7 +26,7 @@ DE_RTOL, DE_ATOL_FRAC = 1e-5, 1e-6
 def algos_for(D):
     out = [0, 2]
     if D <= 16:
-        out.append(1)
+        out += [1, 5]
     if D % 64 == 0 and 64 <= D <= 256:
         out += [3, 4]
     return out
@@ -122,7 +122,7 @@ def test_empty_batch():
 def test_nan_semantics_match_aten_argmin():
     from vq_gan_b200 import ops
     torch.manual_seed(0)
-    for D, algo in ((4, 1), (4, 2), (32, 2), (64, 3), (64, 4)):
+    for D, algo in ((4, 1), (4, 2), (4, 5), (32, 2), (64, 3), (64, 4)):
         E = torch.randn(300, D)
         z = torch.randn(2, D, 4, 4)
         z[0, 1, 2, 3] = float("nan")          # NaN token -> every distance NaN -> index 0

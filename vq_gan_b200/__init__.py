@@ -6,11 +6,12 @@ plus the `vqb200::*` torch.library ops in `vq_gan_b200.ops` and the multi-GPU
 helpers in `vq_gan_b200.distributed`.  The compute lives in lib/libvqb200.so
 (hand-written sm_100a CUDA behind the C ABI of include/vqb200.h).
 """
-from ._cabi import (ALGO_AUTO, ALGO_FP32_TILE, ALGO_LOWD_FMA, ALGO_TCGEN05, ALGO_TCGEN05_F16, LIB_PATH,
+from ._cabi import (ALGO_AUTO, ALGO_FP32_TILE, ALGO_LOWD_FMA, ALGO_TCGEN05, ALGO_TCGEN05_F16, ALGO_TCGEN05_TF32X3,
+                    LIB_PATH,
                     VqbError, lib)
 from . import ops
 from .quantizer import VectorQuantizer
 
 __all__ = ["VectorQuantizer", "ops", "lib", "LIB_PATH", "VqbError", "ALGO_AUTO", "ALGO_LOWD_FMA",
-           "ALGO_FP32_TILE", "ALGO_TCGEN05", "ALGO_TCGEN05_F16"]
+           "ALGO_FP32_TILE", "ALGO_TCGEN05", "ALGO_TCGEN05_F16", "ALGO_TCGEN05_TF32X3"]
 __version__ = "0.1.0"

@@ -11,9 +11,10 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libvqb200.so")
 
 VQB_OK = 0
-ALGO_AUTO, ALGO_LOWD_FMA, ALGO_FP32_TILE, ALGO_TCGEN05, ALGO_TCGEN05_F16 = 0, 1, 2, 3, 4
+ALGO_AUTO, ALGO_LOWD_FMA, ALGO_FP32_TILE, ALGO_TCGEN05, ALGO_TCGEN05_F16, ALGO_TCGEN05_TF32X3 = 0, 1, 2, 3, 4, 5
 ALGO_NAMES = {ALGO_AUTO: "auto", ALGO_LOWD_FMA: "lowd_fma", ALGO_FP32_TILE: "fp32_tile",
-              ALGO_TCGEN05: "tcgen05", ALGO_TCGEN05_F16: "tcgen05_f16"}
+              ALGO_TCGEN05: "tcgen05", ALGO_TCGEN05_F16: "tcgen05_f16",
+              ALGO_TCGEN05_TF32X3: "tcgen05_tf32x3"}
 
 # name -> (restype, argtypes); must list every symbol include/vqb200.h declares
 PROTOTYPES = {

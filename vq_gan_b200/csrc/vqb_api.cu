@@ -71,6 +71,10 @@ extern "C" int vqb_tune(const char* key, int value) {
         set_tc16_cluster(value);
         return VQB_OK;
     }
+    if (key && strcmp(key, "tclow_cluster") == 0 && (value == 1 || value == 2 || value == 4)) {
+        set_tclow_cluster(value);
+        return VQB_OK;
+    }
     set_error("vqb_tune: unknown key or value (%s = %d)", key ? key : "(null)", value);
     return VQB_ERR_INVALID_ARG;
 }
@@ -110,6 +114,7 @@ extern "C" size_t vqb_search_workspace_bytes(int64_t B, int D, int64_t HW, int K
     const int a = resolve_algo(algo, D);
     if (a == VQB_ALGO_TCGEN05) return search_tc_workspace_bytes(B * HW, D, K);
     if (a == VQB_ALGO_TCGEN05_F16) return search_tc16_workspace_bytes(B * HW, D, K);
+    if (a == VQB_ALGO_TCGEN05_TF32X3) return search_tclow_workspace_bytes(B * HW, D, K);
     if (a == VQB_ALGO_FP32_TILE) return search_fp32_workspace_bytes(B * HW);
     return 0;
 }
@@ -168,6 +173,13 @@ extern "C" int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, cons
             }
             return launch_search_tc16(z, B, D, HW, E, K, pack, idx_out, dmin_out, workspace, workspace_bytes,
                                       stats_out, s);
+        case VQB_ALGO_TCGEN05_TF32X3:
+            if (D > kLowDMax) {
+                set_error("VQB_ALGO_TCGEN05_TF32X3 needs D <= %d, got %d", kLowDMax, D);
+                return VQB_ERR_UNSUPPORTED;
+            }
+            return launch_search_tclow(z, B, D, HW, E, K, pack, idx_out, dmin_out, workspace, workspace_bytes,
+                                       stats_out, s);
         default:
             set_error("vqb_search_f32: unknown algo %d", algo);
             return VQB_ERR_INVALID_ARG;

@@ -34,6 +34,7 @@ int sm_count();  // cached per current device
 // ---- packed codebook layout ----------------------------------------------
 // header (int32[64]): [0] first NaN code (K if none) [1] K [2] D [4] float bits of max 0.5|e|^2
 //                      [5] fp16 scale exponent se (e16 = fp16(E * 2^se)) [6] float bits of max|E| [7] bits of max |e - fp16(e)|
+//                      [8] bits of max_k |e_k - eh_k - el_k| and [9] bits of max_k |el_k| (tf32x3 image, D <= 16)
 // half_norm: float[Kpad]  0.5|e_k|^2, +inf for k >= K.  Read as consecutive
 //            (h[2p], h[2p+1]) pairs by the low-D kernel.
 // pairs    : float[Kpad/2][2D]  (D <= 16)  e_d(2p), e_d(2p+1) interleaved per d
@@ -54,9 +55,23 @@ __host__ __device__ inline bool tc_eligible_dim(int D) {
 
 struct PackLayout {
     int K, D, Kpad;
-    size_t off_half_norm, off_pairs, off_ehi, off_elo, off_e16, off_half_norm_fin, total;
+    size_t off_half_norm, off_pairs, off_ehi, off_elo, off_e16, off_half_norm_fin, off_img, total;
     bool has_pairs, has_bf16;
 };
+
+// ---- tf32x3 operand images of the low-D tensor path (vqb_search_tclow.cu) -----------------
+// A row of the contraction has 3D+3 slots, padded to `steps` k-steps of 8 tf32 values:
+//   tokens: [ zh(D) | zl(D) | zh(D) | 1 1 1 | 0.. ]      codes: [ -eh(D) | -eh(D) | -el(D) | h1 h2 h3 | 0.. ]
+// so that one accumulator element is h - z.e (hi*hi + lo*hi + hi*lo terms, half norm in three tf32
+// pieces).  Rows are grouped in tiles of 128; a tile is stored as the exact shared-memory image
+// of a K-major SWIZZLE_NONE UMMA operand: [16-byte k-chunk][8-row group][row][4 floats], i.e.
+// leading byte offset 2048, stride byte offset 128 -- one contiguous bulk copy per tile.
+constexpr int kLowRows = 128;
+__host__ __device__ inline int tclow_steps(int D) { return (3 * D + 3 + 7) / 8; }
+__host__ __device__ inline size_t tclow_tile_floats(int D) { return (size_t)kLowRows * 8 * tclow_steps(D); }
+__host__ __device__ inline size_t tclow_slot_offset(int row_in_tile, int slot) {
+    return (size_t)(slot >> 2) * (kLowRows * 4) + (size_t)(row_in_tile >> 3) * 32 + (row_in_tile & 7) * 4 + (slot & 3);
+}
 
 __host__ __device__ inline PackLayout pack_layout(int K, int D) {
     PackLayout L;
@@ -78,6 +93,8 @@ __host__ __device__ inline PackLayout pack_layout(int K, int D) {
     if (L.has_bf16) off = round_up_z(off + 2 * (size_t)L.Kpad * D, 1024);
     L.off_half_norm_fin = off;  // half norms with a large FINITE pad (1e38) for the key-packing epilogue
     if (L.has_bf16) off = round_up_z(off + sizeof(float) * L.Kpad, 1024);
+    L.off_img = off;  // tf32x3 codebook image (D <= 16)
+    if (L.has_pairs) off = round_up_z(off + sizeof(float) * tclow_tile_floats(D) * (L.Kpad / kLowRows), 1024);
     L.total = off;
     return L;
 }
@@ -105,6 +122,13 @@ __device__ __forceinline__ float min3_f32(float a, float b, float c) {
     return d;
 }
 
+// round-to-nearest tf32 image of an fp32 value (low 13 mantissa bits zero)
+__device__ __forceinline__ float to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -124,6 +148,14 @@ size_t search_tc_workspace_bytes(int64_t n_tokens, int D, int K);
 int launch_search_tc(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                      const void* pack, int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes,
                      int64_t* stats_out, cudaStream_t s);
+size_t search_tclow_workspace_bytes(int64_t n_tokens, int D, int K);
+int launch_search_tclow(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
+                        const void* pack, int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes,
+                        int64_t* stats_out, cudaStream_t s);
+int launch_search_lowd_list(const float* z, int64_t B, int D, int64_t HW, int K, const void* pack,
+                            const int32_t* list, const int32_t* list_count, int64_t* idx_out,
+                            float* dmin_out, cudaStream_t s);
+void set_tclow_cluster(int c);
 size_t search_tc16_workspace_bytes(int64_t n_tokens, int D, int K);
 int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                        const void* pack, int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes,

@@ -15,6 +15,8 @@ __global__ void prepare_header_kernel(int* header, int K, int D) {
         header[5] = 0;  // fp16 scale exponent, written by codebook_prepare_kernel
         header[6] = 0;  // bits of max |E| (codebook_absmax_kernel)
         header[7] = 0;  // bits of max_k |e_k - fp16 image of e_k| (residual of the single-pass tensor path)
+        header[8] = 0;  // bits of max_k |e_k - eh_k - el_k| (tf32x3 image)
+        header[9] = 0;  // bits of max_k |el_k|
     }
 }
 
@@ -93,6 +95,44 @@ __global__ void __launch_bounds__(256) codebook_prepare_kernel(const float* __re
     }
 }
 
+// tf32x3 image of the codebook for the low-D tensor path: one thread per (padded) code row.
+// Runs after codebook_prepare_kernel (reads the half norms it wrote).
+__global__ void __launch_bounds__(128) codebook_image_kernel(const float* __restrict__ E, int K, int D,
+                                                             unsigned char* pack, PackLayout L) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= L.Kpad) return;
+    int* header = reinterpret_cast<int*>(pack);
+    const float* half_norm = reinterpret_cast<const float*>(pack + L.off_half_norm);
+    float* img = reinterpret_cast<float*>(pack + L.off_img) + (size_t)(k / kLowRows) * tclow_tile_floats(D);
+    const int r = k % kLowRows;
+    const int slots = 8 * tclow_steps(D);
+    const bool live = k < K;
+    float res = 0.f, lo2 = 0.f;
+    for (int d = 0; d < D; ++d) {
+        const float v = live ? E[(size_t)k * D + d] : 0.f;
+        const float eh = to_tf32(v);
+        const float rem = v - eh;
+        const float el = to_tf32(rem);
+        const float r2 = rem - el;
+        res = fmaf(r2, r2, res);
+        lo2 = fmaf(el, el, lo2);
+        img[tclow_slot_offset(r, d)] = -eh;
+        img[tclow_slot_offset(r, D + d)] = -eh;
+        img[tclow_slot_offset(r, 2 * D + d)] = -el;
+    }
+    // half norm in three tf32 pieces (33 significant bits >= fp32); padded rows score ~1e38
+    const float h = live ? half_norm[k] : 1e38f;
+    const float h1 = to_tf32(h);
+    const float h2 = to_tf32(h - h1);
+    const float h3 = to_tf32((h - h1) - h2);
+    img[tclow_slot_offset(r, 3 * D + 0)] = h1;
+    img[tclow_slot_offset(r, 3 * D + 1)] = h2;
+    img[tclow_slot_offset(r, 3 * D + 2)] = h3;
+    for (int sl = 3 * D + 3; sl < slots; ++sl) img[tclow_slot_offset(r, sl)] = 0.f;
+    if (live && res == res && res > 0.f && res < INFINITY) atomicMax(&header[8], __float_as_int(sqrtf(res)));
+    if (live && lo2 == lo2 && lo2 > 0.f && lo2 < INFINITY) atomicMax(&header[9], __float_as_int(sqrtf(lo2)));
+}
+
 int launch_codebook_prepare(const float* E, int K, int D, void* pack, cudaStream_t s) {
     const PackLayout L = pack_layout(K, D);
     prepare_header_kernel<<<1, 32, 0, s>>>(reinterpret_cast<int*>(pack), K, D);
@@ -108,6 +148,10 @@ int launch_codebook_prepare(const float* E, int K, int D, void* pack, cudaStream
     const int blocks = (L.Kpad + warps - 1) / warps;
     codebook_prepare_kernel<<<blocks, warps * 32, 0, s>>>(E, K, D, static_cast<unsigned char*>(pack), L);
     VQB_LAUNCH_CHECK("codebook_prepare_kernel");
+    if (L.has_pairs) {
+        codebook_image_kernel<<<(L.Kpad + 127) / 128, 128, 0, s>>>(E, K, D, static_cast<unsigned char*>(pack), L);
+        VQB_LAUNCH_CHECK("codebook_image_kernel");
+    }
     return VQB_OK;
 }
 

@@ -85,7 +85,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 template <int D, int V>
 struct LowDCtx {
     const float* z;
-    int64_t N, HW;
+    int64_t N, HW;             // N = work items: all tokens, or the entries of `list`
+    const int32_t* list;       // optional token list (exact re-search of flagged tokens)
     const float* g_pairs;      // [Kpad/2][2D]
     const float* g_half_norm;  // [Kpad]
     int codes_padded;          // K rounded up to kChunkCodes
@@ -158,8 +159,9 @@ __device__ __forceinline__ void lowd_segment(LowDCtx<D, V>& c, int64_t seg_base)
     int64_t tok[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-        tok[t] = seg_base + (int64_t)t * kLowDThreads + tid;
-        const bool ok = tok[t] < c.N;
+        const int64_t item = seg_base + (int64_t)t * kLowDThreads + tid;
+        const bool ok = item < c.N;
+        tok[t] = ok ? (c.list ? (int64_t)__ldg(c.list + item) : item) : -1;
         const int64_t b = ok ? tok[t] / c.HW : 0;
         const int64_t hw = ok ? tok[t] - b * c.HW : 0;
         const float* zp = c.z + (b * D) * c.HW + hw;
@@ -248,7 +250,7 @@ __device__ __forceinline__ void lowd_segment(LowDCtx<D, V>& c, int64_t seg_base)
 
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-        if (tok[t] < c.N) {
+        if (tok[t] >= 0) {
             int r = best[t];
             if (c.first_nan < c.K) r = (m[t] == INFINITY) ? 0 : c.first_nan;  // NaN code is minimal
             c.idx_out[tok[t]] = r;
@@ -261,14 +263,21 @@ template <int D, int V>
 __global__ void __launch_bounds__(LowDCfg<D, V>::kThreads, LowDCfg<D, V>::kMinBlocks)
     search_lowd_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int K,
                        const unsigned char* __restrict__ pack, PackLayout L, int64_t tokens_per_cta,
+                       const int32_t* __restrict__ list, const int32_t* __restrict__ list_count,
                        int64_t* __restrict__ idx_out, float* __restrict__ dmin_out) {
     using Cfg = LowDCfg<D, V>;
     constexpr int kLowDThreads = Cfg::kThreads;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     LowDCtx<D, V> c;
     c.z = z;
-    c.N = N;
     c.HW = HW;
+    c.list = list;
+    if (list) {  // the number of flagged tokens is only known on the device
+        N = *list_count;
+        tokens_per_cta = (N + gridDim.x - 1) / gridDim.x;
+        tokens_per_cta = (tokens_per_cta + kLowDThreads - 1) / kLowDThreads * kLowDThreads;
+    }
+    c.N = N;
     c.g_pairs = reinterpret_cast<const float*>(pack + L.off_pairs);
     c.g_half_norm = reinterpret_cast<const float*>(pack + L.off_half_norm);
     c.codes_padded = round_up_i(K, kChunkCodes);
@@ -324,7 +333,8 @@ __global__ void __launch_bounds__(LowDCfg<D, V>::kThreads, LowDCfg<D, V>::kMinBl
 
 template <int D, int V>
 static int launch_lowd_t(const float* z, int64_t N, int64_t HW, int K, const void* pack,
-                         int64_t* idx_out, float* dmin_out, cudaStream_t s) {
+                         int64_t* idx_out, float* dmin_out, cudaStream_t s, const int32_t* list = nullptr,
+                         const int32_t* list_count = nullptr) {
     using Cfg = LowDCfg<D, V>;
     constexpr int kLowDThreads = Cfg::kThreads;
     VQB_CUDA_TRY(cudaFuncSetAttribute(search_lowd_kernel<D, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -333,9 +343,9 @@ static int launch_lowd_t(const float* z, int64_t N, int64_t HW, int K, const voi
     const int slots = sm_count() * Cfg::kMinBlocks;  // persistent: one wave of resident CTAs
     int64_t per_cta = (N + slots - 1) / slots;
     per_cta = (per_cta + kLowDThreads - 1) / kLowDThreads * kLowDThreads;
-    const int grid = (int)((N + per_cta - 1) / per_cta);
+    const int grid = list ? slots : (int)((N + per_cta - 1) / per_cta);
     search_lowd_kernel<D, V><<<grid, kLowDThreads, Cfg::kSmemBytes, s>>>(
-        z, N, HW, K, static_cast<const unsigned char*>(pack), L, per_cta, idx_out, dmin_out);
+        z, N, HW, K, static_cast<const unsigned char*>(pack), L, per_cta, list, list_count, idx_out, dmin_out);
     VQB_LAUNCH_CHECK("search_lowd_kernel");
     return VQB_OK;
 }
@@ -356,6 +366,25 @@ int launch_search_lowd(const float* z, int64_t B, int D, int64_t HW, int K, cons
 #define VQB_CASE(d) \
     case d:         \
         return launch_lowd_t<d, 0>(z, N, HW, K, pack, idx_out, dmin_out, s);
+        VQB_CASE(1) VQB_CASE(2) VQB_CASE(3) VQB_CASE(4) VQB_CASE(5) VQB_CASE(6) VQB_CASE(7) VQB_CASE(8)
+        VQB_CASE(9) VQB_CASE(10) VQB_CASE(11) VQB_CASE(12) VQB_CASE(13) VQB_CASE(14) VQB_CASE(15)
+        VQB_CASE(16)
+#undef VQB_CASE
+        default:
+            set_error("low-D search supports 1 <= D <= 16, got %d", D);
+            return VQB_ERR_UNSUPPORTED;
+    }
+}
+
+// exact search of the tokens in a device-side list (the unsure tokens of the tensor path)
+int launch_search_lowd_list(const float* z, int64_t B, int D, int64_t HW, int K, const void* pack,
+                            const int32_t* list, const int32_t* list_count, int64_t* idx_out, float* dmin_out,
+                            cudaStream_t s) {
+    const int64_t N = B * HW;
+    switch (D) {
+#define VQB_CASE(d) \
+    case d:         \
+        return launch_lowd_t<d, 0>(z, N, HW, K, pack, idx_out, dmin_out, s, list, list_count);
         VQB_CASE(1) VQB_CASE(2) VQB_CASE(3) VQB_CASE(4) VQB_CASE(5) VQB_CASE(6) VQB_CASE(7) VQB_CASE(8)
         VQB_CASE(9) VQB_CASE(10) VQB_CASE(11) VQB_CASE(12) VQB_CASE(13) VQB_CASE(14) VQB_CASE(15)
         VQB_CASE(16)

@@ -98,10 +98,11 @@ __global__ void __launch_bounds__(256)
         const int r = ty + 8 * i;  // token within the block
         const int64_t t = t0 + r;
         const int ex = tok_exp[r];
-        const float back = ldexpf(1.f, -ex);
+        // |ex| <= 100: both factors are normal floats, so the products round exactly like ldexpf
+        const float fwd = __int_as_float((127 + ex) << 23), back = __int_as_float((127 - ex) << 23);
         for (int d = 2 * tx; d < D; d += 64) {
             const float a = tile[d][r], b2 = tile[d + 1][r];
-            const __half2 h = __floats2half2_rn(ldexpf(a, ex), ldexpf(b2, ex));
+            const __half2 h = __floats2half2_rn(a * fwd, b2 * fwd);
             const float2 f = __half22float2(h);
             const float da = a - f.x * back, db = b2 - f.y * back;
             res = fmaf(da, da, res);
@@ -456,9 +457,18 @@ __global__ void __launch_bounds__(kT16Threads, 1)
 }
 
 // Exact fp32 re-score of the candidate groups of every token: the 4 codes of group1 and, when
-// present, those of group2 and group3.  A CTA stages 32 tokens x D of z in shared memory (coalesced),
-// then each warp takes 4 tokens; lanes run along the channels so the candidate rows (4 adjacent
-// codebook rows = one contiguous block) are read as full lines.  Lowest index wins ties.
+// present, those of group2 and group3.  A CTA stages 32 tokens x D of z in shared memory (coalesced
+// along the tokens), then each warp takes 4 tokens AT ONCE: lanes run along the channels, the 16
+// (token, code) partial sums are reduced with a transposed butterfly (16 shuffles instead of 80) and
+// the 16 codebook-row streams (full 128-byte lines from L2) are all in flight together.  Tokens with
+// a second / third candidate group (a few %) take a warp-uniform slow path.  Lowest index wins ties.
+__device__ __forceinline__ void lex_min(float& s, int& k, float s2, int k2) {
+    if (s2 < s || (s2 == s && k2 < k)) {
+        s = s2;
+        k = k2;
+    }
+}
+
 __global__ void __launch_bounds__(256)
     rescore_groups_kernel(const float* __restrict__ z, const float* __restrict__ E, const float* __restrict__ half_norm,
                           const int32_t* __restrict__ group1, const int32_t* __restrict__ group2,
@@ -472,50 +482,130 @@ __global__ void __launch_bounds__(256)
         if (tok < N) {
             const int64_t b = tok / HW;
             const float* zp = z + (b * D) * HW + (tok - b * HW);
+#pragma unroll 8
             for (int d = ty; d < D; d += 8) tile[d][tx] = __ldg(zp + (int64_t)d * HW);
         }
     }
+    const int lane = tx, r0 = ty * 4;
+    int g1[4], g2[4];
+    const float* row[16];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int64_t tok = t0 + r0 + t;
+        const bool ok = tok < N;
+        g1[t] = ok ? __ldg(group1 + tok) : 0;
+        g2[t] = ok ? __ldg(group2 + tok) : -1;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            int k = g1[t] * 4 + c;
+            k = k < K ? k : K - 1;  // rows past the end are read in bounds and discarded below
+            row[t * 4 + c] = E + (size_t)k * D + lane;
+        }
+    }
     __syncthreads();
-    const int lane = tx, warp = ty;
-    for (int i = 0; i < 4; ++i) {
-        const int r = warp * 4 + i;
-        const int64_t tok = t0 + r;
-        if (tok >= N) break;  // warp-uniform
-        float best = INFINITY;
-        int best_k = 0x7fffffff;
-        const int first_k = group1[tok] * 4;
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll 2
+    for (int d = 0; d < D; d += 32) {
+        float zv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) zv[t] = tile[d + lane][r0 + t];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fmaf(zv[j >> 2], __ldg(row[j] + d), acc[j]);
+    }
+    // transposed butterfly: afterwards lane L holds the full sum of accumulator (L >> 1) & 15
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float keep = up ? acc[j + 8] : acc[j], send = up ? acc[j] : acc[j + 8];
+            acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float keep = up ? acc[j + 4] : acc[j], send = up ? acc[j] : acc[j + 4];
+            acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float keep = up ? acc[j + 2] : acc[j], send = up ? acc[j] : acc[j + 2];
+            acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool up = lane & 2;
+        const float keep = up ? acc[1] : acc[0], send = up ? acc[0] : acc[1];
+        acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const float dot = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
+    const int my_t = lane >> 3, my_c = (lane >> 1) & 3;  // token / code within the group of this lane's sum
+    const int my_g1 = my_t == 0 ? g1[0] : (my_t == 1 ? g1[1] : (my_t == 2 ? g1[2] : g1[3]));
+    int best_k = my_g1 * 4 + my_c;
+    float best = INFINITY;
+    if (best_k < K) {
+        best = __ldg(half_norm + best_k) - dot;
+        if (best != best) {  // NaN scores never win
+            best = INFINITY;
+            best_k = 0x7fffffff;
+        }
+    } else {
+        best_k = 0x7fffffff;
+    }
+    // (score, index) lexicographic minimum over the 4 codes of the token (lane bits 1 and 2)
+#pragma unroll
+    for (int o = 2; o <= 4; o <<= 1) {
+        const float s2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const int k2 = __shfl_xor_sync(0xffffffffu, best_k, o);
+        lex_min(best, best_k, s2, k2);
+    }
+    // slow path: tokens with more candidate groups (warp-uniform branches)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (g2[t] < 0) continue;
+        const int64_t tok = t0 + r0 + t;
+        float b = __shfl_sync(0xffffffffu, best, t * 8);
+        int bk = __shfl_sync(0xffffffffu, best_k, t * 8);
 #pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-            const int grp = pass == 0 ? group1[tok] : (pass == 1 ? group2[tok] : group3[tok]);
-            if (grp < 0) break;  // warp-uniform
+        for (int pass = 0; pass < 2; ++pass) {
+            const int grp = pass == 0 ? g2[t] : __ldg(group3 + tok);
+            if (grp < 0) break;
             const int k0 = grp * 4;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            float a4[4] = {0.f, 0.f, 0.f, 0.f};
             for (int d = lane; d < D; d += 32) {
-                const float zv = tile[d][r];
+                const float zv = tile[d][r0 + t];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int k = k0 + c;
-                    const float e = (k < K) ? __ldg(E + (size_t)k * D + d) : 0.f;
-                    acc[c] = fmaf(zv, e, acc[c]);
+                    a4[c] = fmaf(zv, (k < K) ? __ldg(E + (size_t)k * D + d) : 0.f, a4[c]);
                 }
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+                for (int o = 16; o > 0; o >>= 1) a4[c] += __shfl_xor_sync(0xffffffffu, a4[c], o);
                 const int k = k0 + c;
                 if (k < K) {
-                    const float dsc = half_norm[k] - acc[c];
-                    // (score, index) lexicographic minimum; NaN scores never win
-                    if (dsc < best || (dsc == best && k < best_k)) {
-                        best = dsc;
-                        best_k = k;
-                    }
+                    const float dsc = __ldg(half_norm + k) - a4[c];
+                    if (dsc == dsc) lex_min(b, bk, dsc, k);
                 }
             }
         }
-        if (best_k == 0x7fffffff) best_k = first_k < K ? first_k : 0;
-        if (lane == 0) {
+        if ((lane >> 3) == t) {
+            best = b;
+            best_k = bk;
+        }
+    }
+    if ((lane & 7) == 0) {
+        const int64_t tok = t0 + r0 + my_t;
+        if (tok < N) {
+            if (best_k == 0x7fffffff) best_k = my_g1 * 4 < K ? my_g1 * 4 : 0;
             idx_out[tok] = best_k;
             if (dmin_out) dmin_out[tok] = best;
         }

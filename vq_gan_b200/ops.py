@@ -22,7 +22,7 @@ LAUNCHES = {"total": 0}
 PROFILE = None
 PROFILE_TAIL = None
 PROFILE_BWD = None
-_KERNELS_PER_CALL = {"prepare": 2, "search": 2, "tail": 2, "backward": 1, "gather": 1, "hist": 2,
+_KERNELS_PER_CALL = {"prepare": 3, "search": 2, "tail": 2, "backward": 1, "gather": 1, "hist": 2,
                      "code_sums": 1, "ema": 2, "keys": 1}
 
 
@@ -37,8 +37,9 @@ def _search_kernels(D: int, algo: int) -> int:
         algo = (_cabi.ALGO_LOWD_FMA if D <= 16 else
                 _cabi.ALGO_TCGEN05_F16 if (D % 64 == 0 and 64 <= D <= 256) else _cabi.ALGO_FP32_TILE)
     # lowd: search + stats; fp32: search (+ finalize) + stats; tcgen05: split, mma, re-score, finalize, stats
+    # tf32x3: split, mma, chunk re-score, list search, stats
     return {_cabi.ALGO_LOWD_FMA: 2, _cabi.ALGO_FP32_TILE: 3, _cabi.ALGO_TCGEN05: 5,
-            _cabi.ALGO_TCGEN05_F16: 6}[algo]
+            _cabi.ALGO_TCGEN05_F16: 6, _cabi.ALGO_TCGEN05_TF32X3: 5}[algo]
 
 
 def _p(t: Optional[Tensor]):
