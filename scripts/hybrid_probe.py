@@ -1,0 +1,43 @@
+"""Feasibility probe: run the CUDA-core search (1 CTA/SM) and the tensor search concurrently on two streams."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vq_gan_b200 import _cabi, ops
+lib = _cabi.lib()
+torch.manual_seed(0)
+B, D, K = 1024, 4, 16384
+z = torch.randn(B, D, 32, 32, device="cuda")
+E = torch.randn(K, D, device="cuda")
+i_ref, _, _ = ops.search(z, E, 1)
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+_cabi.check(lib.vqb_tune(b"lowd_variant", 16 + 1), "tune")
+f = 0.5
+Ba = int(B * f)
+za, zb = z[:Ba].contiguous(), z[Ba:].contiguous()
+for cl in (1, 2):
+    _cabi.check(lib.vqb_tune(b"tclow_cluster", cl), "tune")
+    for mode in ("fma", "tensor", "both", "both"):
+        torch.cuda.synchronize()
+        cur = torch.cuda.current_stream()
+        ev = {k: torch.cuda.Event(enable_timing=True) for k in ("o", "a0", "a1", "b0", "b1", "end")}
+        ev["o"].record()
+        s1.wait_stream(cur); s2.wait_stream(cur)
+        if mode in ("fma", "both"):
+            with torch.cuda.stream(s1):
+                ev["a0"].record()
+                ia, _, _ = ops.search(za, E, 1)
+                ev["a1"].record()
+        if mode in ("tensor", "both"):
+            with torch.cuda.stream(s2):
+                ev["b0"].record()
+                ib, _, _ = ops.search(zb, E, 5)
+                ev["b1"].record()
+        cur.wait_stream(s1); cur.wait_stream(s2)
+        ev["end"].record()
+        torch.cuda.synchronize()
+        o = ev["o"]
+        msg = f"cluster={cl} mode={mode}: total {o.elapsed_time(ev['end']):.3f} ms"
+        if mode in ("fma", "both"):
+            msg += f" | fma [{o.elapsed_time(ev['a0']):.3f}, {o.elapsed_time(ev['a1']):.3f}]"
+        if mode in ("tensor", "both"):
+            msg += f" | tensor [{o.elapsed_time(ev['b0']):.3f}, {o.elapsed_time(ev['b1']):.3f}]"
+        print(msg, flush=True)

@@ -63,7 +63,7 @@ extern "C" int vqb_device_query(int device, int* sm, int* cc_major, int* cc_mino
 }
 
 extern "C" int vqb_tune(const char* key, int value) {
-    if (key && strcmp(key, "lowd_variant") == 0 && value >= 0 && value <= 4) {
+    if (key && strcmp(key, "lowd_variant") == 0 && ((value >= 0 && value <= 4) || (value >= 16 && value <= 19))) {
         set_lowd_variant(value);
         return VQB_OK;
     }
@@ -71,7 +71,7 @@ extern "C" int vqb_tune(const char* key, int value) {
         set_tc16_cluster(value);
         return VQB_OK;
     }
-    if (key && strcmp(key, "tclow_cluster") == 0 && (value == 1 || value == 2 || value == 4)) {
+    if (key && strcmp(key, "tclow_cluster") == 0 && (value == 1 || value == 2 || value == 4 || (value >= 16 && value < 24))) {
         set_tclow_cluster(value);
         return VQB_OK;
     }
@@ -102,16 +102,22 @@ extern "C" int vqb_codebook_prepare_f32(const float* E, int K, int D, void* pack
     return launch_codebook_prepare(E, K, D, pack, static_cast<cudaStream_t>(stream));
 }
 
-static int resolve_algo(int algo, int D) {
+// Measured on B200 (profiles/r01_tclow_vs_fma.txt): the CUDA-core kernel costs ~0.72 ms per 1M tokens x
+// 16384 codes x dimension; the tf32x3 tensor kernel is bound by TMEM traffic at ~2.5-5 ms per 1M x 16384
+// for any D <= 16, with a higher fixed cost.  So: FMA for D <= 4 and for small problems, tensor above.
+static int resolve_algo(int algo, int D, int64_t N = 0, int K = 0) {
     if (algo != VQB_ALGO_AUTO) return algo;
-    if (D <= kLowDMax) return VQB_ALGO_LOWD_FMA;
+    if (D <= kLowDMax) {
+        const bool large = (double)N * (double)K >= 268435456.0;  // 2^28 scores
+        return (D >= 5 && large) ? VQB_ALGO_TCGEN05_TF32X3 : VQB_ALGO_LOWD_FMA;
+    }
     if (tc_eligible_dim(D)) return VQB_ALGO_TCGEN05_F16;  // single fp16 pass + exact re-score: 2.4x the bf16x3 kernel
     return VQB_ALGO_FP32_TILE;
 }
 
 extern "C" size_t vqb_search_workspace_bytes(int64_t B, int D, int64_t HW, int K, int algo) {
     if (B < 0 || HW < 0 || D <= 0 || K <= 0) return 0;
-    const int a = resolve_algo(algo, D);
+    const int a = resolve_algo(algo, D, B * HW, K);
     if (a == VQB_ALGO_TCGEN05) return search_tc_workspace_bytes(B * HW, D, K);
     if (a == VQB_ALGO_TCGEN05_F16) return search_tc16_workspace_bytes(B * HW, D, K);
     if (a == VQB_ALGO_TCGEN05_TF32X3) return search_tclow_workspace_bytes(B * HW, D, K);
@@ -144,7 +150,7 @@ extern "C" int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, cons
         return VQB_ERR_INVALID_ARG;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int a = resolve_algo(algo, D);
+    const int a = resolve_algo(algo, D, N, K);
     int rc;
     switch (a) {
         case VQB_ALGO_LOWD_FMA:

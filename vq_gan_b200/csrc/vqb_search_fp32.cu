@@ -213,7 +213,7 @@ int launch_search_fp32(const float* z, int64_t B, int D, int64_t HW, const float
     // only splits when there are too few token tiles to fill the chip twice
     int splits = 1;
     if (token_list) {
-        splits = code_tiles < 32 ? code_tiles : 32;
+        splits = code_tiles < 128 ? code_tiles : 128;  // a few hundred tokens: one item per SM slot is latency-bound
     } else if (tiles < 2 * sms) {
         int64_t want = (2 * sms + tiles - 1) / tiles;
         splits = (int)(want < code_tiles ? want : code_tiles);

@@ -46,7 +46,10 @@ struct LowDCfg {
 };
 
 static int g_lowd_variant = 0;
-void set_lowd_variant(int v) { g_lowd_variant = v; }
+static int g_lowd_ctas_per_sm = 0;  // 0 = the variant's own residency; 1 leaves room for a co-running kernel
+void set_lowd_variant(int v) {
+    if (v >= 16) g_lowd_ctas_per_sm = v - 16; else g_lowd_variant = v;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -83,7 +86,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 template <int D, int V>
-struct LowDCtx {
+struct LowDCtx {  // (kList kernels fill `list`; the dense kernels leave it null and never read it)
     const float* z;
     int64_t N, HW;             // N = work items: all tokens, or the entries of `list`
     const int32_t* list;       // optional token list (exact re-search of flagged tokens)
@@ -148,7 +151,7 @@ __device__ __forceinline__ void load_pair(const float* p, unsigned long long (&e
 }
 
 // T tokens per thread: tokens seg_base + t*kThreads + tid
-template <int D, int V, int T>
+template <int D, int V, int T, bool kList>
 __device__ __forceinline__ void lowd_segment(LowDCtx<D, V>& c, int64_t seg_base) {
     using Cfg = LowDCfg<D, V>;
     constexpr int kLowDThreads = Cfg::kThreads;
@@ -161,7 +164,7 @@ __device__ __forceinline__ void lowd_segment(LowDCtx<D, V>& c, int64_t seg_base)
     for (int t = 0; t < T; ++t) {
         const int64_t item = seg_base + (int64_t)t * kLowDThreads + tid;
         const bool ok = item < c.N;
-        tok[t] = ok ? (c.list ? (int64_t)__ldg(c.list + item) : item) : -1;
+        tok[t] = ok ? (kList ? (int64_t)__ldg(c.list + item) : item) : -1;
         const int64_t b = ok ? tok[t] / c.HW : 0;
         const int64_t hw = ok ? tok[t] - b * c.HW : 0;
         const float* zp = c.z + (b * D) * c.HW + hw;
@@ -259,7 +262,7 @@ __device__ __forceinline__ void lowd_segment(LowDCtx<D, V>& c, int64_t seg_base)
     }
 }
 
-template <int D, int V>
+template <int D, int V, bool kList>
 __global__ void __launch_bounds__(LowDCfg<D, V>::kThreads, LowDCfg<D, V>::kMinBlocks)
     search_lowd_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int K,
                        const unsigned char* __restrict__ pack, PackLayout L, int64_t tokens_per_cta,
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(LowDCfg<D, V>::kThreads, LowDCfg<D, V>::kMinBl
     c.z = z;
     c.HW = HW;
     c.list = list;
-    if (list) {  // the number of flagged tokens is only known on the device
+    if constexpr (kList) {  // the number of flagged tokens is only known on the device
         N = *list_count;
         tokens_per_cta = (N + gridDim.x - 1) / gridDim.x;
         tokens_per_cta = (tokens_per_cta + kLowDThreads - 1) / kLowDThreads * kLowDThreads;
@@ -312,23 +315,23 @@ __global__ void __launch_bounds__(LowDCfg<D, V>::kThreads, LowDCfg<D, V>::kMinBl
 
     int64_t base = start;
     while (q >= TM) {
-        lowd_segment<D, V, TM>(c, base);
+        lowd_segment<D, V, TM, kList>(c, base);
         base += (int64_t)TM * kLowDThreads;
         q -= TM;
     }
     if constexpr (TM >= 8) {
         if (q & 4) {
-            lowd_segment<D, V, 4>(c, base);
+            lowd_segment<D, V, 4, kList>(c, base);
             base += 4 * kLowDThreads;
         }
     }
     if constexpr (TM >= 4) {
         if (q & 2) {
-            lowd_segment<D, V, 2>(c, base);
+            lowd_segment<D, V, 2, kList>(c, base);
             base += 2 * kLowDThreads;
         }
     }
-    if (q & 1) lowd_segment<D, V, 1>(c, base);
+    if (q & 1) lowd_segment<D, V, 1, kList>(c, base);
 }
 
 template <int D, int V>
@@ -337,14 +340,16 @@ static int launch_lowd_t(const float* z, int64_t N, int64_t HW, int K, const voi
                          const int32_t* list_count = nullptr) {
     using Cfg = LowDCfg<D, V>;
     constexpr int kLowDThreads = Cfg::kThreads;
-    VQB_CUDA_TRY(cudaFuncSetAttribute(search_lowd_kernel<D, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)Cfg::kSmemBytes));
+    auto kernel = list ? search_lowd_kernel<D, V, true> : search_lowd_kernel<D, V, false>;
+    VQB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
     const PackLayout L = pack_layout(K, D);
-    const int slots = sm_count() * Cfg::kMinBlocks;  // persistent: one wave of resident CTAs
+    // persistent: one wave of resident CTAs
+    const int slots = sm_count() * ((g_lowd_ctas_per_sm > 0 && g_lowd_ctas_per_sm < Cfg::kMinBlocks) ? g_lowd_ctas_per_sm
+                                                                                                      : Cfg::kMinBlocks);
     int64_t per_cta = (N + slots - 1) / slots;
     per_cta = (per_cta + kLowDThreads - 1) / kLowDThreads * kLowDThreads;
     const int grid = list ? slots : (int)((N + per_cta - 1) / per_cta);
-    search_lowd_kernel<D, V><<<grid, kLowDThreads, Cfg::kSmemBytes, s>>>(
+    kernel<<<grid, kLowDThreads, Cfg::kSmemBytes, s>>>(
         z, N, HW, K, static_cast<const unsigned char*>(pack), L, per_cta, list, list_count, idx_out, dmin_out);
     VQB_LAUNCH_CHECK("search_lowd_kernel");
     return VQB_OK;

@@ -40,11 +40,15 @@ constexpr uint32_t kT16Idesc = (1u << 4)  // accumulator f32; A, B = f16 (format
 // ---------------------------------------------------------------------------
 constexpr int kSplitDimMax = 256;
 
+// NCH = D / 32 (2, 4, 6, 8): every loop below has a compile-time trip count, so the addresses are
+// immediates (the run-time-D version spent 3 of 4 issue slots on address arithmetic)
+template <int NCH>
 __global__ void __launch_bounds__(256)
-    split16_tokens_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW, const int* __restrict__ header,
+    split16_tokens_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const int* __restrict__ header,
                           __half* __restrict__ z16, float* __restrict__ inv_scale, float* __restrict__ znorm,
                           float* __restrict__ zres) {
-    __shared__ float tile[kSplitDimMax][33];
+    constexpr int D = 32 * NCH;
+    __shared__ float tile[D][33];
     __shared__ float part_a[8][32];
     __shared__ float part_b[8][32];
     __shared__ int tok_exp[32];
@@ -52,21 +56,23 @@ __global__ void __launch_bounds__(256)
     const int64_t t0 = (int64_t)blockIdx.x * 32;
     const int64_t tok = t0 + tx;
     const bool ok = tok < N;
-    int64_t off = 0;
-    if (ok) {
-        const int64_t b = tok / HW;
-        off = (b * D) * HW + (tok - b * HW);
-    }
     // pass 1: stage the tile, per-token max |z| and sum of squares
     float sq = 0.f, mx = 0.f;
     bool finite = true;
-    for (int d = ty; d < D; d += 8) {
-        const float v = ok ? __ldg(z + off + (int64_t)d * HW) : 0.f;
-        tile[d][tx] = v;
-        sq = fmaf(v, v, sq);
-        const float a = fabsf(v);
-        finite &= (a < INFINITY);  // false for NaN as well
-        mx = fmaxf(mx, a);
+    {
+        const int64_t b = ok ? tok / HW : 0;
+        const float* zp = z + (b * D) * HW + (ok ? tok - b * HW : 0) + (int64_t)ty * HW;
+        const int64_t step = 8 * HW;
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) {
+            const float v = ok ? __ldg(zp) : 0.f;
+            zp += step;
+            tile[ty + 8 * i][tx] = v;
+            sq = fmaf(v, v, sq);
+            const float a = fabsf(v);
+            finite &= (a < INFINITY);  // false for NaN as well
+            mx = fmaxf(mx, a);
+        }
     }
     part_a[ty][tx] = sq;
     part_b[ty][tx] = finite ? mx : INFINITY;
@@ -92,29 +98,35 @@ __global__ void __launch_bounds__(256)
         }
     }
     __syncthreads();
-    // pass 2: scale, convert, write token-major rows; accumulate the rounding residual
-    float res = 0.f;
+    // pass 2: scale, convert, write token-major rows; accumulate the rounding residual.  Lane L reads
+    // channels L and L+32 of a 64-channel block (conflict-free), one shuffle pairs neighbours up so
+    // that even lanes store channels (L, L+1) and odd lanes (L+31, L+32) as one half2 each.
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = ty + 8 * i;  // token within the block
         const int64_t t = t0 + r;
         const int ex = tok_exp[r];
         // |ex| <= 100: both factors are normal floats, so the products round exactly like ldexpf
         const float fwd = __int_as_float((127 + ex) << 23), back = __int_as_float((127 - ex) << 23);
-        for (int d = 2 * tx; d < D; d += 64) {
-            const float a = tile[d][r], b2 = tile[d + 1][r];
-            const __half2 h = __floats2half2_rn(a * fwd, b2 * fwd);
-            const float2 f = __half22float2(h);
-            const float da = a - f.x * back, db = b2 - f.y * back;
+        float res = 0.f;
+#pragma unroll
+        for (int j = 0; j < NCH / 2; ++j) {
+            const float a = tile[64 * j + tx][r], b2 = tile[64 * j + 32 + tx][r];
+            const __half ha = __float2half_rn(a * fwd), hb = __float2half_rn(b2 * fwd);
+            const float da = a - __half2float(ha) * back, db = b2 - __half2float(hb) * back;
             res = fmaf(da, da, res);
             res = fmaf(db, db, res);
-            if (t < N) *reinterpret_cast<__half2*>(z16 + (size_t)t * D + d) = h;
+            const bool odd = tx & 1;
+            const unsigned short mine = __half_as_ushort(odd ? ha : hb);  // what the partner needs
+            const unsigned short got = (unsigned short)__shfl_xor_sync(0xffffffffu, (int)mine, 1);
+            const __half2 h = odd ? __halves2half2(__ushort_as_half(got), hb) : __halves2half2(ha, __ushort_as_half(got));
+            const int ch = 64 * j + (odd ? 32 + tx - 1 : tx);
+            if (t < N) *reinterpret_cast<__half2*>(z16 + (size_t)t * D + ch) = h;
         }
         // the 32 lanes of this warp hold the residual of token r: reduce and store
-        float tot = res;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        if (tx == 0 && t < N) zres[t] = sqrtf(tot);
-        res = 0.f;
+        for (int o = 16; o > 0; o >>= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
+        if (tx == 0 && t < N) zres[t] = sqrtf(res);
     }
 }
 
@@ -469,21 +481,28 @@ __device__ __forceinline__ void lex_min(float& s, int& k, float s2, int k2) {
     }
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(256)
     rescore_groups_kernel(const float* __restrict__ z, const float* __restrict__ E, const float* __restrict__ half_norm,
                           const int32_t* __restrict__ group1, const int32_t* __restrict__ group2,
-                          const int32_t* __restrict__ group3, int64_t N, int D, int64_t HW, int K,
+                          const int32_t* __restrict__ group3, int64_t N, int64_t HW, int K,
                           int64_t* __restrict__ idx_out, float* __restrict__ dmin_out) {
-    __shared__ float tile[kSplitDimMax][33];
+    constexpr int D = 32 * NCH;
+    // row stride 36 floats: the 4 tokens of a warp are one aligned 16-byte read, stores stay conflict-free
+    __shared__ __align__(16) float tile[D][36];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t t0 = (int64_t)blockIdx.x * 32;
     {
         const int64_t tok = t0 + tx;
         if (tok < N) {
             const int64_t b = tok / HW;
-            const float* zp = z + (b * D) * HW + (tok - b * HW);
-#pragma unroll 8
-            for (int d = ty; d < D; d += 8) tile[d][tx] = __ldg(zp + (int64_t)d * HW);
+            const float* zp = z + (b * D) * HW + (tok - b * HW) + (int64_t)ty * HW;
+            const int64_t step = 8 * HW;
+#pragma unroll
+            for (int i = 0; i < D / 8; ++i) {
+                tile[ty + 8 * i][tx] = __ldg(zp);
+                zp += step;
+            }
         }
     }
     const int lane = tx, r0 = ty * 4;
@@ -506,13 +525,12 @@ __global__ void __launch_bounds__(256)
     float acc[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-#pragma unroll 2
-    for (int d = 0; d < D; d += 32) {
-        float zv[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) zv[t] = tile[d + lane][r0 + t];
+    for (int c = 0; c < NCH; ++c) {
+        const float4 z4 = *reinterpret_cast<const float4*>(&tile[32 * c + lane][r0]);
+        const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = fmaf(zv[j >> 2], __ldg(row[j] + d), acc[j]);
+        for (int j = 0; j < 16; ++j) acc[j] = fmaf(zv[j >> 2], __ldg(row[j] + 32 * c), acc[j]);
     }
     // transposed butterfly: afterwards lane L holds the full sum of accumulator (L >> 1) & 15
     {
@@ -731,8 +749,16 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
     int32_t* counts = reinterpret_cast<int32_t*>(wsb + w.off_counts);
 
     VQB_CUDA_TRY(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), s));
-    split16_tokens_kernel<<<(unsigned)((N + 31) / 32), 256, 0, s>>>(z, N, D, HW, reinterpret_cast<const int*>(pk), z16,
-                                                                   inv, znorm, zres);
+    {
+        const unsigned blocks = (unsigned)((N + 31) / 32);
+        const int* hdr = reinterpret_cast<const int*>(pk);
+        switch (D / 32) {
+            case 2: split16_tokens_kernel<2><<<blocks, 256, 0, s>>>(z, N, HW, hdr, z16, inv, znorm, zres); break;
+            case 4: split16_tokens_kernel<4><<<blocks, 256, 0, s>>>(z, N, HW, hdr, z16, inv, znorm, zres); break;
+            case 6: split16_tokens_kernel<6><<<blocks, 256, 0, s>>>(z, N, HW, hdr, z16, inv, znorm, zres); break;
+            default: split16_tokens_kernel<8><<<blocks, 256, 0, s>>>(z, N, HW, hdr, z16, inv, znorm, zres); break;
+        }
+    }
     VQB_LAUNCH_CHECK("split16_tokens_kernel");
 
     // codebook maps: the box is the slice one CTA of the cluster fetches (256, 128 or 64 rows)
@@ -770,8 +796,19 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
     }
     if (rc != VQB_OK) return rc;
     // exact fp32 choice among the 4 (or 8) certified candidates of every token
-    rescore_groups_kernel<<<(unsigned)((N + 31) / 32), 256, 0, s>>>(z, E, p.half_norm, p.group1, p.group2, p.group3, N, D,
-                                                                    HW, K, idx_out, dmin_out);
+    {
+        const unsigned blocks = (unsigned)((N + 31) / 32);
+#define VQB_RESCORE(nch)                                                                                              \
+    rescore_groups_kernel<nch><<<blocks, 256, 0, s>>>(z, E, p.half_norm, p.group1, p.group2, p.group3, N, HW, K, idx_out, \
+                                                      dmin_out)
+        switch (D / 32) {
+            case 2: VQB_RESCORE(2); break;
+            case 4: VQB_RESCORE(4); break;
+            case 6: VQB_RESCORE(6); break;
+            default: VQB_RESCORE(8); break;
+        }
+#undef VQB_RESCORE
+    }
     VQB_LAUNCH_CHECK("rescore_groups_kernel");
     // ambiguous tokens: full exact fp32 search
     rc = launch_search_fp32(z, B, D, HW, E, K, pack, p.full_list, p.full_count, N, wsb + w.off_keys, w.keys_bytes,

@@ -270,14 +270,14 @@ __global__ void __launch_bounds__(kLowThreads, 1) search_tclow_kernel(LowParams 
                 tc_mbar_wait(tm_full + acc, (g >> 2) & 1);
                 tc_fence_after();
                 const uint32_t t_acc = tmem_base + lane_addr + acc * kLowBN;
-                uint32_t ra[32], rb[32];
-                tmem_ld32_issue(t_acc, ra);
+                // one TMEM load in flight per warp: the partner warp of this scheduler (other tile
+                // parity) covers the latency; double buffering measured no faster -- the kernel is
+                // bound by TMEM traffic (64 KB written by the MMAs + 64 KB read back per 128x128 tile)
+                uint32_t r[32];
 #pragma unroll
                 for (int j = 0; j < kLowBN / kLowChunk; ++j) {
-                    uint32_t(&r)[32] = (j & 1) ? rb : ra;
-                    uint32_t(&rn)[32] = (j & 1) ? ra : rb;
+                    tmem_ld32_issue(t_acc + j * kLowChunk, r);
                     tmem_ld_wait();
-                    if (j + 1 < kLowBN / kLowChunk) tmem_ld32_issue(t_acc + (j + 1) * kLowChunk, rn);
                     // minimum of the 32 scores: five independent FMNMX3 chains, then combined
                     float c0 = min3_f32(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
                     float c1 = min3_f32(__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5]));
@@ -365,7 +365,8 @@ __global__ void __launch_bounds__(256)
     float my_min = INFINITY;
 #pragma unroll 4
     for (int t = 0; t < n_here; ++t) {
-        const int k = __shfl_sync(0xffffffffu, my_chunk, t) * kLowChunk + lane;
+        const int chunk_t = __shfl_sync(0xffffffffu, my_chunk, t);
+        const int k = chunk_t * kLowChunk + lane;
         float zt[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) zt[d] = __shfl_sync(0xffffffffu, nz[d], t);  // all lanes take part
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(256)
         const unsigned hit = __ballot_sync(0xffffffffu, s == m && k < K);
         const int first = hit ? (__ffs(hit) - 1) : 0;
         if (lane == t) {
-            my_idx = __shfl_sync(0xffffffffu, my_chunk, t) * kLowChunk + first;
+            my_idx = chunk_t * kLowChunk + first;
             my_min = m;
         }
     }
@@ -441,7 +442,10 @@ size_t search_tclow_workspace_bytes(int64_t n_tokens, int D, int K) {
 }
 
 static int g_tclow_cluster = 2;
-void set_tclow_cluster(int c) { g_tclow_cluster = c; }
+static int g_tclow_debug = 0;  // bit 0: skip the tensor kernel, bit 1: skip the chunk re-score, bit 2: skip the list search
+void set_tclow_cluster(int c) {
+    if (c >= 16) g_tclow_debug = c - 16; else g_tclow_cluster = c;
+}
 
 template <int CL>
 static int launch_tclow_cl(const LowParams& p0, cudaStream_t s) {
@@ -453,8 +457,12 @@ static int launch_tclow_cl(const LowParams& p0, cudaStream_t s) {
     if (stages > n_n_tiles) stages = n_n_tiles;
     if (stages < 2) stages = 2;
     p.n_stages = stages;
-    const size_t smem = 1024 + (2 + (size_t)stages) * tile_bytes + 512 + 2 * kLowRows * 4 * sizeof(float);
+    size_t smem = 1024 + (2 + (size_t)stages) * tile_bytes + 512 + 2 * kLowRows * 4 * sizeof(float);
+    // every CTA allocates all 512 TMEM columns: never let two of them share an SM
+    if (smem < 116 * 1024) smem = 116 * 1024;
     VQB_CUDA_TRY(cudaFuncSetAttribute(search_tclow_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VQB_CUDA_TRY(cudaFuncSetAttribute(search_tclow_kernel<CL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      (int)cudaSharedmemCarveoutMaxShared));
     const int n_m_tiles = (int)((p.N + kLowRows - 1) / kLowRows);
     int grid = n_m_tiles < sm_count() ? n_m_tiles : sm_count();
     grid = (grid + CL - 1) / CL * CL;
@@ -509,13 +517,18 @@ static int launch_tclow_d(const float* z, int64_t N, int64_t HW, const float* E,
     p.chunk = chunk;
     p.list = list;
     p.list_count = count;
-    int rc;
-    switch (g_tclow_cluster) {
-        case 1: rc = launch_tclow_cl<1>(p, s); break;
-        case 4: rc = launch_tclow_cl<4>(p, s); break;
-        default: rc = launch_tclow_cl<2>(p, s); break;
+    int rc = VQB_OK;
+    if (g_tclow_debug & 1) {
+        VQB_CUDA_TRY(cudaMemsetAsync(chunk, 0, sizeof(int32_t) * (size_t)N, s));
+    } else {
+        switch (g_tclow_cluster) {
+            case 1: rc = launch_tclow_cl<1>(p, s); break;
+            case 4: rc = launch_tclow_cl<4>(p, s); break;
+            default: rc = launch_tclow_cl<2>(p, s); break;
+        }
     }
     if (rc != VQB_OK) return rc;
+    if (g_tclow_debug & 2) return VQB_OK;
     const unsigned warps = (unsigned)((N + 31) / 32);
     rescore_chunk_kernel<D><<<(warps + 7) / 8, 256, 0, s>>>(z, E, reinterpret_cast<const float*>(pk + L.off_half_norm),
                                                             chunk, N, HW, K, idx_out, dmin_out);
@@ -557,8 +570,10 @@ int launch_search_tclow(const float* z, int64_t B, int D, int64_t HW, const floa
     // unsure tokens: exact search by the CUDA-core kernel itself (bit-identical to VQB_ALGO_LOWD_FMA)
     const int32_t* list = reinterpret_cast<const int32_t*>(wsb + w.off_list);
     const int32_t* count = reinterpret_cast<const int32_t*>(wsb + w.off_count);
-    rc = launch_search_lowd_list(z, B, D, HW, K, pack, list, count, idx_out, dmin_out, s);
-    if (rc != VQB_OK) return rc;
+    if (!(g_tclow_debug & 4)) {
+        rc = launch_search_lowd_list(z, B, D, HW, K, pack, list, count, idx_out, dmin_out, s);
+        if (rc != VQB_OK) return rc;
+    }
     if (stats_out) {
         tclow_stats_kernel<<<1, 1, 0, s>>>(stats_out, count);
         VQB_LAUNCH_CHECK("tclow_stats_kernel");

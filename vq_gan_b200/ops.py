@@ -31,10 +31,10 @@ def _count(kind: str, kernels: int = 0) -> None:
     LAUNCHES[kind] = LAUNCHES.get(kind, 0) + 1
 
 
-def _search_kernels(D: int, algo: int) -> int:
+def _search_kernels(D: int, algo: int, N: int = 0, K: int = 0) -> int:
     """libvqb200 kernels one vqb_search_f32 call launches (mirrors resolve_algo in vqb_api.cu)."""
     if algo == _cabi.ALGO_AUTO:
-        algo = (_cabi.ALGO_LOWD_FMA if D <= 16 else
+        algo = ((_cabi.ALGO_TCGEN05_TF32X3 if (D >= 5 and N * K >= 1 << 28) else _cabi.ALGO_LOWD_FMA) if D <= 16 else
                 _cabi.ALGO_TCGEN05_F16 if (D % 64 == 0 and 64 <= D <= 256) else _cabi.ALGO_FP32_TILE)
     # lowd: search + stats; fp32: search (+ finalize) + stats; tcgen05: split, mma, re-score, finalize, stats
     # tf32x3: split, mma, chunk re-score, list search, stats
@@ -103,7 +103,7 @@ def _search_into(z: Tensor, weight: Tensor, algo: int, want_dmin: bool):
     if prof is not None:
         ev1.record()
         prof.append((ev0, ev1))
-    _count("search", _search_kernels(D, algo))
+    _count("search", _search_kernels(D, algo, B * HW, K))
     return idx, dmin, stats
 
 
