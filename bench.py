@@ -37,6 +37,18 @@ BETA = 0.25
 N_ROTATE = 8  # distinct input sets cycled through so the working set exceeds the 126 MB L2
 
 
+def load_traffic(kernel, workload):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (None if not captured
+    for this workload)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            ent = json.load(f).get(kernel)
+        return ent["bytes"] if ent and ent.get("workload") == workload else None
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -374,6 +386,7 @@ def run_gpu_arm(args):
     # host->device on a side stream while the current step computes (every step still pays
     # its own H2D copy and D2H read-back inside the timed region)
     copy_stream = torch.cuda.Stream(device=device)
+    d2h_stream = torch.cuda.Stream(device=device)
 
     def prefetch(i):
         with torch.cuda.stream(copy_stream):
@@ -396,7 +409,13 @@ def run_gpu_arm(args):
             sq = torch.tensor([loss_dict["codebook_loss"] * z.numel()], device=device)
             dE, hist, s = vdist.allreduce_stats(weight.grad, usage, sq, average_dE=True)
             weight.grad.copy_(dE)
-        idx_host.copy_(idx, non_blocking=True)
+        # indices go back on their own stream so the copy overlaps the next step (still inside the timed region)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(ready)
+            idx_host.copy_(idx, non_blocking=True)
+            idx.record_stream(d2h_stream)
         return loss_dict["vq_loss"].item(), nxt
 
     e2e_steps = max(3, min(args.steps, 20))
@@ -408,6 +427,7 @@ def run_gpu_arm(args):
     e0.record()
     for i in range(e2e_steps):
         _, staged = e2e_step(3 + i, staged)
+    torch.cuda.current_stream().wait_stream(d2h_stream)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -446,10 +466,12 @@ def run_gpu_arm(args):
                                                5: "search_tclow_kernel"}.get(algo, str(algo)),
                     "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                     "traffic": None, "kernel_ms": s_ms, "algorithmic_flops_per_launch": flops,
+                    "algorithmic_bytes_per_launch": tokens * (4 * D + 8) + 4 * K * D,
                     "executed_flops_factor": factor,
                     "frac_executed": achieved * factor / peak,
                     "peak_source": peak_note,
                     "step_share": s_ms * len(search_ms) / ms_total if search_ms else None}
+        roofline["traffic"] = load_traffic(roofline["kernel"], args.workload)
         # HBM-side kernels: algorithmic bytes per token 8D+8 (tail) and 12D+8 (+ dE once) (backward)
         hbm = {}
         for name, ms_list, nbytes in (("gather_loss_st_kernel", tail_ms, tokens * (8 * D + 8)),
@@ -458,6 +480,7 @@ def run_gpu_arm(args):
                 t = statistics.mean(ms_list)
                 hbm[name] = {"kernel_ms": t, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (t * 1e-3) / 1e9,
                              "peak_gbs": peaks["hbm_gbs"], "frac": nbytes / (t * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                             "traffic": load_traffic(name, args.workload),
                              "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})"}
         line = {
             "metric": "vq_lookup_tokens_per_sec", "value": tokens * world * args.steps / (ms_total * 1e-3),

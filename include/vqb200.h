@@ -137,6 +137,17 @@ VQB_API int vqb_pack_argmin_keys(const float* dmin, const int64_t* idx, int64_t 
 VQB_API int vqb_unpack_argmin_keys(const int64_t* keys, int64_t n, int64_t* idx_out, float* dmin_out,
                            vqb_stream_t stream);
 
+/* ---- compact index maps (next row N3: VQVAE.encode_to_indices / decode_from_indices,
+ * vq_vae.py:162-190, cached like preprocess_latents.py:236-238 but 1-4 bytes per token) ----
+ * vqb_index_bytes(K): 1 (K <= 256), 2 (K <= 65536) or 4.
+ * narrow: codes_out[i] = (uintN) idx[i]; err_flag set to 1 when an index is outside [0, K).
+ * widen : idx_out[i] = (int64) codes[i]. */
+VQB_API int vqb_index_bytes(int K);
+VQB_API int vqb_indices_narrow(const int64_t* idx, int64_t n, int K, void* codes_out, int elem_bytes,
+                       int* err_flag, vqb_stream_t stream);
+VQB_API int vqb_indices_widen(const void* codes, int64_t n, int elem_bytes, int64_t* idx_out,
+                      vqb_stream_t stream);
+
 /* ---- measurement --------------------------------------------------------
  * FP32 FMA peak microbenchmark (the low-D roofline denominator): launches a
  * register-resident FFMA (packed=0) or FFMA2 (packed=1) loop on every SM and

@@ -10,7 +10,7 @@ E = torch.randn(K, D, device="cuda")
 i_ref, _, _ = ops.search(z, E, 1)
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 _cabi.check(lib.vqb_tune(b"lowd_variant", 16 + 1), "tune")
-f = 0.5
+f = float(os.environ.get('FRAC', '0.5'))
 Ba = int(B * f)
 za, zb = z[:Ba].contiguous(), z[Ba:].contiguous()
 for cl in (1, 2):
@@ -21,16 +21,25 @@ for cl in (1, 2):
         ev = {k: torch.cuda.Event(enable_timing=True) for k in ("o", "a0", "a1", "b0", "b1", "end")}
         ev["o"].record()
         s1.wait_stream(cur); s2.wait_stream(cur)
-        if mode in ("fma", "both"):
+        def run_fma():
             with torch.cuda.stream(s1):
                 ev["a0"].record()
-                ia, _, _ = ops.search(za, E, 1)
+                ops.search(za, E, 1)
                 ev["a1"].record()
-        if mode in ("tensor", "both"):
+        def run_tensor():
             with torch.cuda.stream(s2):
                 ev["b0"].record()
-                ib, _, _ = ops.search(zb, E, 5)
+                ops.search(zb, E, 5)
                 ev["b1"].record()
+        order = os.environ.get("ORDER", "fma_first")
+        if mode == "fma":
+            run_fma()
+        elif mode == "tensor":
+            run_tensor()
+        elif order == "fma_first":
+            run_fma(); run_tensor()
+        else:
+            run_tensor(); run_fma()
         cur.wait_stream(s1); cur.wait_stream(s2)
         ev["end"].record()
         torch.cuda.synchronize()

@@ -58,6 +58,42 @@ def test_c2_full_size_properties():
     np.testing.assert_allclose(dE.numpy(), (-0.25 * dz).numpy(), rtol=1e-3, atol=1e-7)
 
 
+def test_c2_tensor_path_is_bit_identical_to_fma_kernel():
+    """algo 5 (tf32x3 tcgen05 + certified chunk + exact FMA re-score) must return exactly the indices
+    and minimum scores of algo 1 at full size, for a realistic and for the tie-heavy reference init."""
+    from vq_gan_b200 import ops
+    z, E = _c2()
+    zc = z.cuda()
+    K = E.shape[0]
+    books = {"normal": E.cuda(),
+             "reference_init": ((torch.rand(K, 4, generator=torch.Generator().manual_seed(3)) * 2 - 1) / K).cuda()}
+    for name, Ec in books.items():
+        i1, d1, _ = ops.search(zc, Ec, 1)
+        i5, d5, st = ops.search(zc, Ec, 5)
+        print(f"c2 {name}: unsure tokens re-searched exactly = {int(st[0])} of {i1.numel()}")
+        assert int(st[1]) == 5
+        assert torch.equal(i1, i5) and torch.equal(d1, d5)
+    # other low dimensions (different numbers of k-steps), ragged token count, K not a multiple of 128
+    for D, Kx, B, HW in ((1, 700, 3, 331), (3, 1000, 5, 1024), (8, 5000, 9, 777), (16, 4099, 7, 1024)):
+        g = torch.Generator().manual_seed(D)
+        zz = torch.randn(B, D, HW, generator=g).cuda()
+        EE = torch.randn(Kx, D, generator=g).cuda()
+        i1, d1, _ = ops.search(zz, EE, 1)
+        i5, d5, _ = ops.search(zz, EE, 5)
+        assert torch.equal(i1, i5) and torch.equal(d1, d5), (D, Kx)
+    # NaN / inf tokens and a NaN code follow the same ATen rules as algo 1
+    zz = torch.randn(4, 4, 16, 16, generator=torch.Generator().manual_seed(9))
+    zz[0, 1, 2, 3] = float("nan")
+    zz[1, 0, 0, 0] = float("inf")
+    EE = torch.randn(777, 4, generator=torch.Generator().manual_seed(10))
+    for nan_code in (False, True):
+        if nan_code:
+            EE[123, 2] = float("nan")
+        i1, _, _ = ops.search(zz.cuda(), EE.cuda(), 1)
+        i5, _, _ = ops.search(zz.cuda(), EE.cuda(), 5)
+        assert torch.equal(i1, i5)
+
+
 def test_c3_slice_tensor_path_against_fp32_kernel():
     from vq_gan_b200 import ops
     g = torch.Generator().manual_seed(0)

@@ -230,3 +230,28 @@ def test_argmin_keys_bit_exact_with_oracle():
     assert torch.equal(keys.cpu(), orc.argmin_key(d.cpu(), i.cpu() + 1000))
     idx, dm = ops.unpack_argmin_keys(keys)
     assert torch.equal(idx, i + 1000) and torch.equal(dm.cpu().abs(), d.cpu().abs())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [128, 256, 257, 16384, 65536, 65537])
+def test_compact_index_roundtrip_on_device(K):
+    """Row N3: device-side narrow/widen of index maps is bit-exact and flags out-of-range indices."""
+    from vq_gan_b200 import indexio, ops
+    g = torch.Generator().manual_seed(K)
+    for shape in ((3, 7, 5), (2, 32, 32), (1, 1, 1), (5, 33, 17)):
+        idx = torch.randint(0, K, shape, generator=g)
+        idx.view(-1)[0], idx.view(-1)[-1] = 0, K - 1
+        blob = indexio.pack_indices(idx.cuda(), K)
+        want = indexio.pack_indices(idx, K)  # host path
+        assert blob["codes"].dtype == want["codes"].dtype == indexio.index_dtype(K)
+        assert torch.equal(blob["codes"].view(torch.uint8), want["codes"].view(torch.uint8))
+        back = indexio.unpack_indices(blob, device="cuda")
+        assert back.dtype == torch.int64 and torch.equal(back.cpu(), idx)
+    # misaligned views take the scalar tail path
+    idx = torch.randint(0, K, (4099,), generator=g).cuda()
+    codes, err = ops.indices_narrow(idx[3:], K)
+    assert int(err.item()) == 0 and torch.equal(ops.indices_widen(codes), idx[3:])
+    bad = idx.clone()
+    bad[77] = K
+    with pytest.raises(ValueError):
+        indexio.pack_indices(bad.view(1, 1, -1), K)

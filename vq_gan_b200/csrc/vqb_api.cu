@@ -75,6 +75,12 @@ extern "C" int vqb_tune(const char* key, int value) {
         set_tclow_cluster(value);
         return VQB_OK;
     }
+    if (key && (strcmp(key, "bwd_pass_channels") == 0 || strcmp(key, "fwd_pass_channels") == 0) &&
+        (value == 64 || value == 128 || value == 192 || value == 256)) {
+        if (key[0] == 'f') value += 1024;
+        set_bwd_pass_cap(value);
+        return VQB_OK;
+    }
     set_error("vqb_tune: unknown key or value (%s = %d)", key ? key : "(null)", value);
     return VQB_ERR_INVALID_ARG;
 }

@@ -138,7 +138,7 @@ struct LowParams {
 };
 
 template <int CL>
-__global__ void __launch_bounds__(kLowThreads, 1) search_tclow_kernel(LowParams p) {
+__global__ void __launch_bounds__(kLowThreads, 2) search_tclow_kernel(LowParams p) {  // <= 85 registers: can share an SM with the CUDA-core kernel
     extern __shared__ unsigned char smem_unaligned[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) &
                                                            ~(uintptr_t)1023);

@@ -214,54 +214,60 @@ __device__ __forceinline__ void tile_load_tokens(TileTokens& tt, const int64_t* 
     }
 }
 
-// codebook rows of the CTA's 32 tokens, channels [d0, d0+dc) -> tile[channel][token]
+// codebook rows of the CTA's 32 tokens, channels [d0, d0+DC) -> tile[channel][token]
+// (warp w stages tokens 4w..4w+3; lane = channel: full 128-byte lines, immediate offsets)
+template <int DC>
 __device__ __forceinline__ void tile_fill_codes(float (*tile)[kTileTok + 1], const TileTokens& tt,
-                                                const float* __restrict__ E, int D, int d0, int dc) {
+                                                const float* __restrict__ E, int D, int d0) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int t = warp * 4 + i;
-        const float* erow = E + (size_t)tt.code[t] * D + d0;
-#pragma unroll 8
-        for (int c = lane; c < dc; c += 32) tile[c][t] = __ldg(erow + c);
+        const float* erow = E + (size_t)tt.code[t] * D + d0 + lane;
+#pragma unroll
+        for (int c = 0; c < DC / 32; ++c) tile[lane + 32 * c][t] = __ldg(erow + 32 * c);
     }
 }
 
-__global__ void __launch_bounds__(256)
+// DC = channels per pass (64, 128, 192 or 256, a divisor of D): every loop has a compile-time trip
+// count, z (DRAM) is requested BEFORE the wait on the codebook rows (L2) so both latencies overlap.
+template <int DC>
+__global__ void __launch_bounds__(256, DC <= 128 ? 4 : 2)
     gather_loss_st_tiled_kernel(const float* __restrict__ z, const float* __restrict__ E,
                                 const int64_t* __restrict__ idx, int64_t N, int D, int64_t HW, int K,
                                 float* __restrict__ zq_out, double* __restrict__ partials,
                                 int* __restrict__ err_flag) {
-    __shared__ float tile[kTileDimMax][kTileTok + 1];
+    constexpr int R = DC / 8;  // channels per thread per pass
+    __shared__ float tile[DC][kTileTok + 1];
     __shared__ TileTokens tt;
     __shared__ double warp_part[8];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     tile_load_tokens(tt, idx, N, D, HW, K, err_flag);
     __syncthreads();
     const int64_t off = tt.off[tx];
+    const int64_t step = 8 * HW;
     float sq = 0.f;
-    for (int d0 = 0; d0 < D; d0 += kTileDimMax) {
-        const int dc = (D - d0) < kTileDimMax ? (D - d0) : kTileDimMax;
-        if (d0 > 0) __syncthreads();
-        tile_fill_codes(tile, tt, E, D, d0, dc);
+    for (int d0 = 0; d0 < D; d0 += DC) {
+        float zv[R];
+        if (off >= 0) {
+            const float* zp = z + off + (int64_t)(d0 + ty) * HW;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                zv[i] = __ldg(zp);
+                zp += step;
+            }
+        }
+        if (d0 > 0) __syncthreads();  // the previous pass is done with the tile
+        tile_fill_codes<DC>(tile, tt, E, D, d0);
         __syncthreads();
         if (off >= 0) {
-            for (int c0 = 0; c0 < dc; c0 += 128) {  // 16 channels per thread per round
-                float zv[16];
+            float* qp = zq_out + off + (int64_t)(d0 + ty) * HW;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int c = c0 + ty + 8 * i;
-                    zv[i] = c < dc ? __ldg(z + off + (int64_t)(d0 + c) * HW) : 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int c = c0 + ty + 8 * i;
-                    if (c < dc) {
-                        const float diff = __fsub_rn(tile[c][tx], zv[i]);
-                        zq_out[off + (int64_t)(d0 + c) * HW] = __fadd_rn(zv[i], diff);
-                        sq = fmaf(diff, diff, sq);
-                    }
-                }
+            for (int i = 0; i < R; ++i) {
+                const float diff = __fsub_rn(tile[ty + 8 * i][tx], zv[i]);
+                *qp = __fadd_rn(zv[i], diff);
+                qp += step;
+                sq = fmaf(diff, diff, sq);
             }
         }
     }
@@ -276,19 +282,22 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-__global__ void __launch_bounds__(256)
+template <int DC>
+__global__ void __launch_bounds__(256, DC <= 64 ? 4 : (DC <= 128 ? 3 : 2))
     backward_tiled_kernel(const float* __restrict__ z, const float* __restrict__ E,
                           const int64_t* __restrict__ idx, const float* __restrict__ g_zq,
                           const float* __restrict__ g_vq, float beta, float norm, int64_t N, int D,
                           int64_t HW, int K, float* __restrict__ dz_out, float* __restrict__ dE,
                           unsigned long long* __restrict__ hist) {
-    __shared__ float tile[kTileDimMax][kTileTok + 1];
+    constexpr int R = DC / 8;
+    __shared__ float tile[DC][kTileTok + 1];
     __shared__ TileTokens tt;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int lane = tx, warp = ty;
     tile_load_tokens(tt, idx, N, D, HW, K, nullptr);
     __syncthreads();
     const int64_t off = tt.off[tx];
+    const int64_t step = 8 * HW;
     const float gv = g_vq ? __ldg(g_vq) : 0.f;
     const float gbeta = __fmul_rn(gv, beta);
     if (hist != nullptr && ty == 0) {
@@ -300,31 +309,40 @@ __global__ void __launch_bounds__(256)
             if (lane == __ffs(peers) - 1) atomicAdd(hist + k, (unsigned long long)__popc(peers));
         }
     }
-    for (int d0 = 0; d0 < D; d0 += kTileDimMax) {
-        const int dc = (D - d0) < kTileDimMax ? (D - d0) : kTileDimMax;
-        if (d0 > 0) __syncthreads();
-        tile_fill_codes(tile, tt, E, D, d0, dc);
+    for (int d0 = 0; d0 < D; d0 += DC) {
+        float zv[R], gz[R];
+        if (off >= 0) {
+            const int64_t o = off + (int64_t)(d0 + ty) * HW;
+            const float* zp = z + o;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                zv[i] = __ldg(zp);
+                zp += step;
+            }
+            if (g_zq) {
+                const float* gp = g_zq + o;
+#pragma unroll
+                for (int i = 0; i < R; ++i) {
+                    gz[i] = __ldg(gp);
+                    gp += step;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < R; ++i) gz[i] = 0.f;
+            }
+        }
+        if (d0 > 0) __syncthreads();  // the scatter of the previous pass is done with the tile
+        tile_fill_codes<DC>(tile, tt, E, D, d0);
         __syncthreads();
         if (off >= 0) {
-            for (int c0 = 0; c0 < dc; c0 += 64) {  // 8 channels per thread per round, z and g
-                float zv[8], gz[8];
+            float* dp = dz_out + off + (int64_t)(d0 + ty) * HW;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c = c0 + ty + 8 * i;
-                    const int64_t o = off + (int64_t)(d0 + c) * HW;
-                    zv[i] = c < dc ? __ldg(z + o) : 0.f;
-                    gz[i] = (c < dc && g_zq) ? __ldg(g_zq + o) : 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c = c0 + ty + 8 * i;
-                    if (c < dc) {
-                        const float e = tile[c][tx];
-                        const float t = __fmul_rn(__fmul_rn(norm, __fsub_rn(zv[i], e)), gv);
-                        dz_out[off + (int64_t)(d0 + c) * HW] = __fadd_rn(gz[i], t);
-                        tile[c][tx] = __fmul_rn(__fmul_rn(norm, __fsub_rn(e, zv[i])), gbeta);
-                    }
-                }
+            for (int i = 0; i < R; ++i) {
+                const float e = tile[ty + 8 * i][tx];
+                const float t = __fmul_rn(__fmul_rn(norm, __fsub_rn(zv[i], e)), gv);
+                *dp = __fadd_rn(gz[i], t);
+                dp += step;
+                tile[ty + 8 * i][tx] = __fmul_rn(__fmul_rn(norm, __fsub_rn(e, zv[i])), gbeta);
             }
         }
         __syncthreads();
@@ -335,13 +353,22 @@ __global__ void __launch_bounds__(256)
             for (int i = 0; i < 2; ++i) {
                 const int t = warp * 4 + i * 2 + half;
                 if (tt.off[t] >= 0) {
-                    float* drow = dE + (size_t)tt.code[t] * D + d0;
-                    for (int c = 4 * l16; c < dc; c += 64)
-                        red_add_v4(drow + c, tile[c + 0][t], tile[c + 1][t], tile[c + 2][t], tile[c + 3][t]);
+                    float* drow = dE + (size_t)tt.code[t] * D + d0 + 4 * l16;
+#pragma unroll
+                    for (int c = 0; c < DC; c += 64)
+                        red_add_v4(drow + c, tile[c + 4 * l16 + 0][t], tile[c + 4 * l16 + 1][t], tile[c + 4 * l16 + 2][t],
+                                   tile[c + 4 * l16 + 3][t]);
                 }
             }
         }
     }
+}
+
+// largest pass width (channels) that divides D; the backward keeps z and g in registers -> half of it
+static int tiled_pass_width(int D, int cap) {
+    for (int dc = cap; dc >= 64; dc -= 64)
+        if (D % dc == 0) return dc;
+    return 64;
 }
 
 // ---------------------------------------------------------------------------
@@ -560,6 +587,14 @@ static int check_shape(int64_t B, int D, int64_t HW, int K) {
     return VQB_OK;
 }
 
+static int g_bwd_pass_cap = 64;   // measured best on B200 (profiles/r01_tail_pass_width_sweep.txt)
+static int g_fwd_pass_cap = 64;
+namespace vqb {
+void set_bwd_pass_cap(int c) {
+    if (c >= 1024) g_fwd_pass_cap = c - 1024; else g_bwd_pass_cap = c;
+}
+}  // namespace vqb
+
 extern "C" size_t vqb_tail_partials_bytes(int64_t n_tokens) {
     return sizeof(double) * (size_t)((n_tokens + 31) / 32 + 1);
 }
@@ -590,7 +625,15 @@ extern "C" int vqb_gather_loss_st_f32(const float* z, const float* E, const int6
     double* parts = static_cast<double*>(partials);
     if (D % 64 == 0) {
         const int64_t tb = (N + kTileTok - 1) / kTileTok;
-        gather_loss_st_tiled_kernel<<<(unsigned)tb, 256, 0, s>>>(z, E, idx, N, D, HW, K, zq_out, parts, err_flag);
+#define VQB_GATHER(dc) \
+    gather_loss_st_tiled_kernel<dc><<<(unsigned)tb, 256, 0, s>>>(z, E, idx, N, D, HW, K, zq_out, parts, err_flag)
+        switch (tiled_pass_width(D, g_fwd_pass_cap)) {
+            case 256: VQB_GATHER(256); break;
+            case 192: VQB_GATHER(192); break;
+            case 128: VQB_GATHER(128); break;
+            default: VQB_GATHER(64); break;
+        }
+#undef VQB_GATHER
         VQB_LAUNCH_CHECK("gather_loss_st_tiled_kernel");
         loss_finalize_kernel<<<1, 256, 0, s>>>(parts, tb, 1.0 / ((double)N * D), beta, loss_out);
         VQB_LAUNCH_CHECK("loss_finalize_kernel");
@@ -628,8 +671,16 @@ extern "C" int vqb_backward_f32(const float* z, const float* E, const int64_t* i
     const bool v4 = vec4_ok(D, E) && (!dE_accum || (reinterpret_cast<uintptr_t>(dE_accum) & 15u) == 0);
     if (D % 64 == 0 && (!dE_accum || (reinterpret_cast<uintptr_t>(dE_accum) & 15u) == 0)) {
         const int64_t tb = (N + kTileTok - 1) / kTileTok;
-        backward_tiled_kernel<<<(unsigned)tb, 256, 0, s>>>(z, E, idx, g_zq, g_vq, beta, norm, N, D, HW, K, dz_out,
-                                                           dE_accum, hist);
+#define VQB_BWD(dc)                                                                                            \
+    backward_tiled_kernel<dc><<<(unsigned)tb, 256, 0, s>>>(z, E, idx, g_zq, g_vq, beta, norm, N, D, HW, K, dz_out, \
+                                                           dE_accum, hist)
+        switch (tiled_pass_width(D, g_bwd_pass_cap)) {
+            case 256: VQB_BWD(256); break;
+            case 192: VQB_BWD(192); break;
+            case 128: VQB_BWD(128); break;
+            default: VQB_BWD(64); break;
+        }
+#undef VQB_BWD
         VQB_LAUNCH_CHECK("backward_tiled_kernel");
         return VQB_OK;
     }

@@ -364,6 +364,53 @@ def _(keys):
     return torch.empty_like(keys), keys.new_empty(keys.shape, dtype=torch.float32)
 
 
+_NARROW_DTYPES = {1: torch.uint8, 2: torch.uint16, 4: torch.int32}
+
+
+@torch.library.custom_op("vqb200::indices_narrow", mutates_args=())
+def indices_narrow(indices: Tensor, num_embeddings: int) -> Tuple[Tensor, Tensor]:
+    """(codes uint8/uint16/int32 of the same shape, err int32[1]) -- compact index map (row N3)."""
+    if not indices.is_cuda or indices.dtype != torch.int64:
+        raise RuntimeError("indices must be a CUDA int64 tensor")
+    indices = indices.contiguous()
+    w = lib().vqb_index_bytes(int(num_embeddings))
+    if w == 0:
+        raise RuntimeError("num_embeddings must be positive")
+    codes = torch.empty(indices.shape, dtype=_NARROW_DTYPES[w], device=indices.device)
+    err = torch.zeros(1, dtype=torch.int32, device=indices.device)
+    with torch.cuda.device(indices.device):
+        check(lib().vqb_indices_narrow(_p(indices), indices.numel(), int(num_embeddings), _p(codes), w,
+                                       _p(err), _stream()), "vqb_indices_narrow")
+        _count("keys")
+    return codes, err
+
+
+@indices_narrow.register_fake
+def _(indices, num_embeddings):
+    w = 1 if num_embeddings <= 256 else (2 if num_embeddings <= 65536 else 4)
+    return (indices.new_empty(indices.shape, dtype=_NARROW_DTYPES[w]),
+            indices.new_empty((1,), dtype=torch.int32))
+
+
+@torch.library.custom_op("vqb200::indices_widen", mutates_args=())
+def indices_widen(codes: Tensor) -> Tensor:
+    """int64 indices from a compact index map (uint8 / uint16 / int32)."""
+    if not codes.is_cuda or codes.dtype not in (torch.uint8, torch.uint16, torch.int32):
+        raise RuntimeError("codes must be a CUDA uint8 / uint16 / int32 tensor")
+    codes = codes.contiguous()
+    out = torch.empty(codes.shape, dtype=torch.int64, device=codes.device)
+    with torch.cuda.device(codes.device):
+        check(lib().vqb_indices_widen(_p(codes), codes.numel(), codes.element_size(), _p(out), _stream()),
+              "vqb_indices_widen")
+        _count("keys")
+    return out
+
+
+@indices_widen.register_fake
+def _(codes):
+    return codes.new_empty(codes.shape, dtype=torch.int64)
+
+
 def fma_peak_tflops(packed: bool, iters: int = 4096, repeats: int = 5) -> float:
     """Measured FP32 FMA peak of the current device (roofline denominator for the
     low-D search): best of `repeats`, CUDA events on the current stream."""
