@@ -32,7 +32,9 @@ WORKLOADS = {
     "c5": (56, 256, 32, 32, 65536, "bulk encode: 56 images (57344 tokens) per rank per step, codebook 65536 x d=256 "
                                    "sharded over the ranks, all-gather + local search + MIN reduce-scatter"),
 }
-CPU_CHUNK_TOKENS = {"c2": 32768, "c3": 16384, "c1": 4096, "c4": 4096, "c5": 4096}
+WORKLOADS["n1"] = (1024, 256, 32, 32, 256, "next row N1: pre_quant_conv-style 1x1 convolution 256 -> 256 channels on 1M tokens "
+                   "(NCHW fp32, 3xTF32 tcgen05), forward only; K here = output channels")
+CPU_CHUNK_TOKENS = {"c2": 32768, "c3": 16384, "c1": 4096, "c4": 4096, "c5": 4096, "n1": 65536}
 BETA = 0.25
 N_ROTATE = 8  # distinct input sets cycled through so the working set exceeds the 126 MB L2
 
@@ -125,6 +127,14 @@ def cpu_step_fn(workload):
     _, D, H, W, K, _ = WORKLOADS[workload]
     chunk = CPU_CHUNK_TOKENS[workload]
     B = max(chunk // (H * W), 1)
+    if workload == "n1":  # the reference layer itself: nn.Conv2d(cin, cout, 1) (vq_vae.py:75), forward
+        conv = torch.nn.Conv2d(D, K, 1)
+        xc = torch.randn(B, D, H, W, generator=torch.Generator().manual_seed(0))
+
+        def fn_conv():
+            with torch.no_grad():
+                return conv(xc)
+        return fn_conv, B * H * W
     z = torch.randn(B, D, H, W, generator=torch.Generator().manual_seed(0))
     E = torch.randn(K, D, generator=torch.Generator().manual_seed(1))
     g = torch.randn(B, D, H, W, generator=torch.Generator().manual_seed(2))
@@ -214,6 +224,92 @@ def gpu_strawman_tokens_per_s(workload, device):
     b.record()
     b.synchronize()
     return B * H * W * 5 / (a.elapsed_time(b) * 1e-3)
+
+
+def run_conv(args, world, rank, local_rank, device, B, Cin, H, W, Cout, desc, peaks):
+    """n1: the 1x1 convolution next to the quantizer (vq_vae.py:74-79,115), forward, HBM-bound."""
+    import torch.distributed as dist
+    from vq_gan_b200 import ops
+    tokens = B * H * W
+    g = torch.Generator(device=device).manual_seed(100 + rank)
+    xs = [torch.randn(B, Cin, H, W, device=device, generator=g) for _ in range(2)]
+    wt = torch.randn(Cout, Cin, device=device, generator=g) / Cin ** 0.5
+    bs = torch.randn(Cout, device=device, generator=g)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    warmup = max(args.warmup, 3)
+    for i in range(warmup):
+        ops.conv1x1(xs[i % 2], wt, bs)
+    barrier()
+    launches0 = ops.LAUNCHES["total"]
+    ops.PROFILE_CONV = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ev0.record()
+        for i in range(args.steps):
+            ops.conv1x1(xs[i % 2], wt, bs)
+        ev1.record()
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    k_ms = statistics.mean(a.elapsed_time(b) for a, b in ops.PROFILE_CONV)
+    ops.PROFILE_CONV = None
+    if world > 1:
+        t = torch.tensor([ms_total], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    # end to end: pinned host activations in, result's checksum out, every step
+    x_host = torch.randn(B, Cin, H, W).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        float(ops.conv1x1(x_host.to(device, non_blocking=True), wt, bs).sum())
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        float(ops.conv1x1(x_host.to(device, non_blocking=True), wt, bs).sum())
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if rank == 0:
+        nbytes = tokens * (Cin + Cout) * 4 + 4 * Cin * Cout
+        flops = 2.0 * tokens * Cin * Cout
+        line = {
+            "metric": "vq_lookup_tokens_per_sec", "value": tokens * world * args.steps / (ms_total * 1e-3),
+            "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"n1: {desc}", "tokens_per_gpu_per_step": tokens, "Cin": Cin, "Cout": Cout,
+                       "l2": "2 rotating input sets (2147 MB) > 126 MB L2"},
+            "roofline": {"bound": "hbm", "kernel": "conv1x1_tc_kernel", "achieved": nbytes / (k_ms * 1e-3) / 1e9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "traffic": None, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": nbytes,
+                         "tensor_tflops_algorithmic": flops / (k_ms * 1e-3) / 1e12, "executed_flops_factor": 3,
+                         "tensor_frac_executed": 3 * flops / (k_ms * 1e-3) / 1e12 / (peaks["bf16_tflops_sustained"] / 2)},
+            "e2e": {"value": tokens * world * e2e_steps / (e2e_ms * 1e-3), "unit": "tokens/s",
+                    "h2d_bytes_per_step": tokens * Cin * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                    "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": ops.LAUNCHES["total"] - launches0, "clocks": clk.summary(),
+        }
+        if world == 1:
+            torch.set_num_threads(os.cpu_count() or 1)
+            xc = torch.randn(64, Cin, H, W)
+            conv = torch.nn.Conv2d(Cin, Cout, 1)
+            conv(xc)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                conv(xc)
+            dt = (time.perf_counter() - t0) / 3
+            line["cpu_baseline"] = {"value": 64 * H * W / dt, "unit": "tokens/s", "cores": torch.get_num_threads(),
+                                    "kind": "port", "sample": "nn.Conv2d(256, 256, 1) forward on 65536 tokens, torch CPU fp32"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+        dist.destroy_process_group()
 
 
 def run_sharded_encode(args, world, rank, local_rank, device, B, D, H, W, K, desc, peaks):
@@ -307,6 +403,8 @@ def run_gpu_arm(args):
     peaks = load_peaks()
     if args.workload == "c5":
         return run_sharded_encode(args, world, rank, local_rank, device, B, D, H, W, K, desc, peaks)
+    if args.workload == "n1":
+        return run_conv(args, world, rank, local_rank, device, B, D, H, W, K, desc, peaks)
 
     vq = VectorQuantizer(K, D, BETA, lazy_stats=True, algo=args.algo).to(device)
     with torch.no_grad():

@@ -148,6 +148,17 @@ VQB_API int vqb_indices_narrow(const int64_t* idx, int64_t n, int K, void* codes
 VQB_API int vqb_indices_widen(const void* codes, int64_t n, int elem_bytes, int64_t* idx_out,
                       vqb_stream_t stream);
 
+/* ---- 1x1 convolution either side of the quantizer (next row N1) -----------------------
+ * `pre_quant_conv` / `post_quant_conv` = nn.Conv2d(Cin, Cout, kernel_size=1) (vq_vae.py:74-79,115,121):
+ *   y[B, Cout, HW] = W[Cout, Cin] . x[B, Cin, HW] + bias[Cout]     (bias nullable)
+ * algo 0 = auto, 1 = 3xTF32 tcgen05 path (needs Cin % 32 == 0, Cout % 16 == 0, Cout <= 256;
+ * fp32-level accuracy: relative error ~2^-21), 2 = CUDA-core path (any shape).
+ * workspace: vqb_conv1x1_workspace_bytes(Cin, Cout) bytes, 256-byte aligned (split weights). */
+VQB_API size_t vqb_conv1x1_workspace_bytes(int Cin, int Cout);
+VQB_API int vqb_conv1x1_f32(const float* x, int64_t B, int Cin, int64_t HW, const float* W,
+                    const float* bias, int Cout, float* y, void* workspace, size_t workspace_bytes,
+                    int algo, vqb_stream_t stream);
+
 /* ---- measurement --------------------------------------------------------
  * FP32 FMA peak microbenchmark (the low-D roofline denominator): launches a
  * register-resident FFMA (packed=0) or FFMA2 (packed=1) loop on every SM and

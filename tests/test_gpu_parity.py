@@ -255,3 +255,42 @@ def test_compact_index_roundtrip_on_device(K):
     bad[77] = K
     with pytest.raises(ValueError):
         indexio.pack_indices(bad.view(1, 1, -1), K)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,Cin,Cout,H,W,algo", [
+    (2, 256, 256, 32, 32, 1), (3, 64, 256, 16, 16, 1), (2, 256, 64, 32, 32, 1), (1, 32, 16, 5, 7, 1),
+    (5, 128, 48, 9, 11, 1), (2, 96, 256, 32, 32, 0), (2, 4, 256, 32, 32, 0), (2, 256, 4, 32, 32, 0),
+    (1, 7, 5, 3, 3, 2), (2, 256, 256, 8, 8, 2)])
+def test_conv1x1_matches_torch_fp32(B, Cin, Cout, H, W, algo):
+    """Row N1: pre/post_quant_conv (nn.Conv2d(cin, cout, 1), vq_vae.py:74-79) forward + backward against
+    torch's fp32 CPU convolution.  Tolerance: 3xTF32 keeps ~2^-21 relative error per product, so
+    |err| <= 2e-6 * sum|w||x| elementwise (checked as atol on the fp64 magnitude bound)."""
+    from vq_gan_b200 import QuantConv1x1
+    g = torch.Generator().manual_seed(B * 1000 + Cin + Cout)
+    ref = torch.nn.Conv2d(Cin, Cout, 1)
+    with torch.no_grad():
+        ref.weight.copy_(torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5)
+        ref.bias.copy_(torch.randn(Cout, generator=g))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    gy = torch.randn(B, Cout, H, W, generator=g)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(gy)
+    mine = QuantConv1x1(Cin, Cout, algo=algo)
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    mine = mine.cuda()
+    xc = x.cuda().requires_grad_(True)
+    y = mine(xc)
+    y.backward(gy.cuda())
+    with torch.no_grad():
+        bound = (torch.nn.functional.conv2d(x.abs().double(), ref.weight.abs().double())
+                 + ref.bias.abs().double().view(1, -1, 1, 1))
+        gbound = torch.nn.functional.conv2d(gy.abs().double(), ref.weight.abs().double().transpose(0, 1))
+    err = (y.detach().cpu().double() - yr.detach().double()).abs()
+    assert y.shape == yr.shape and y.is_contiguous()
+    assert float((err / bound).max()) < 2e-6, float((err / bound).max())
+    gerr = (xc.grad.cpu().double() - xr.grad.double()).abs()
+    assert float((gerr / gbound.clamp_min(1e-30)).max()) < 2e-6
+    assert torch.allclose(mine.weight.grad.cpu(), ref.weight.grad, rtol=1e-4, atol=1e-4 * float(ref.weight.grad.abs().max()))
+    assert torch.allclose(mine.bias.grad.cpu(), ref.bias.grad, rtol=1e-4, atol=1e-4 * float(ref.bias.grad.abs().max()))

@@ -46,6 +46,9 @@ PROTOTYPES = {
     "vqb_index_bytes": (c_int, [c_int]),
     "vqb_indices_narrow": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "vqb_indices_widen": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "vqb_conv1x1_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "vqb_conv1x1_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p,
+                                c_void_p, c_size_t, c_int, c_void_p]),
     "vqb_ubench_launch": (c_int, [c_int, c_int, c_void_p, c_void_p, POINTER(c_double), c_void_p]),
     "vqb_fma_peak_launch": (c_int, [c_int, c_int, c_void_p, POINTER(c_double), c_void_p]),
 }

@@ -81,6 +81,10 @@ extern "C" int vqb_tune(const char* key, int value) {
         set_bwd_pass_cap(value);
         return VQB_OK;
     }
+    if (key && strcmp(key, "conv_debug") == 0 && value >= 0 && value < 16) {
+        set_conv_debug(value);
+        return VQB_OK;
+    }
     set_error("vqb_tune: unknown key or value (%s = %d)", key ? key : "(null)", value);
     return VQB_ERR_INVALID_ARG;
 }

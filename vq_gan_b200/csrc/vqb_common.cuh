@@ -157,6 +157,7 @@ int launch_search_lowd_list(const float* z, int64_t B, int D, int64_t HW, int K,
                             float* dmin_out, cudaStream_t s);
 void set_tclow_cluster(int c);
 void set_bwd_pass_cap(int c);
+void set_conv_debug(int v);
 size_t search_tc16_workspace_bytes(int64_t n_tokens, int D, int K);
 int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                        const void* pack, int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes,

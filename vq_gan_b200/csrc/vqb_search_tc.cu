@@ -398,6 +398,27 @@ int make_tc_map(CUtensorMap* map, const void* base, uint64_t rows, int D, uint32
     return VQB_OK;
 }
 
+// rows x cols fp32 row-major, box = 32 columns (128 B) x box_rows, 128B swizzle (tf32 operands)
+int make_tc_map_f32(CUtensorMap* map, const void* base, uint64_t rows, int cols, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is unavailable in this driver");
+        return VQB_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {32u, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (fp32) failed with %d (rows=%llu cols=%d)", (int)r, (unsigned long long)rows, cols);
+        return VQB_ERR_CUDA;
+    }
+    return VQB_OK;
+}
+
 template <int NKB>
 static int launch_tc_t(const CUtensorMap& mzh, const CUtensorMap& mzl, const CUtensorMap& meh,
                        const CUtensorMap& mel, const TcParams& p, cudaStream_t s) {

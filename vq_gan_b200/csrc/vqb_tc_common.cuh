@@ -141,6 +141,8 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // host: 2-D tensor map over a row-major [rows, D] 16-bit matrix, box = 64 columns x box_rows, 128B swizzle
 int make_tc_map(CUtensorMap* map, const void* base, uint64_t rows, int D, uint32_t box_rows, bool fp16);
 
+int make_tc_map_f32(CUtensorMap* map, const void* base, uint64_t rows, int cols, uint32_t box_rows);
+
 // exact fp32 score of the chosen code (kernel in vqb_search_tc.cu)
 int launch_exact_score(const float* z, const float* E, const float* half_norm, const int64_t* idx, int64_t N, int D,
                        int64_t HW, int K, float* dmin_out, cudaStream_t s);

@@ -23,7 +23,7 @@ PROFILE = None
 PROFILE_TAIL = None
 PROFILE_BWD = None
 _KERNELS_PER_CALL = {"prepare": 3, "search": 2, "tail": 2, "backward": 1, "gather": 1, "hist": 2,
-                     "code_sums": 1, "ema": 2, "keys": 1}
+                     "code_sums": 1, "ema": 2, "keys": 1, "conv": 2}
 
 
 def _count(kind: str, kernels: int = 0) -> None:
@@ -409,6 +409,80 @@ def indices_widen(codes: Tensor) -> Tensor:
 @indices_widen.register_fake
 def _(codes):
     return codes.new_empty(codes.shape, dtype=torch.int64)
+
+
+# ---------------------------------------------------------------------------
+# 1x1 convolution either side of the quantizer (row N1; vq_vae.py:74-79,115,121)
+# ---------------------------------------------------------------------------
+PROFILE_CONV = None
+
+
+@torch.library.custom_op("vqb200::conv1x1", mutates_args=())
+def conv1x1(x: Tensor, weight: Tensor, bias: Optional[Tensor], algo: int = 0) -> Tensor:
+    """y[B,Cout,*spatial] = weight[Cout,Cin] . x[B,Cin,*spatial] + bias (fp32, NCHW in and out)."""
+    _need_cuda_f32(x, "x")
+    _need_cuda_f32(weight, "weight")
+    x = x.contiguous()
+    weight = weight.reshape(weight.shape[0], -1).contiguous()
+    if x.dim() < 2 or int(x.shape[1]) != int(weight.shape[1]):
+        raise RuntimeError(f"conv1x1: input channels {tuple(x.shape)} do not match the weight {tuple(weight.shape)}")
+    if bias is not None:
+        _need_cuda_f32(bias, "bias")
+        bias = bias.contiguous()
+    B, Cin, Cout = int(x.shape[0]), int(x.shape[1]), int(weight.shape[0])
+    HW = x.numel() // max(B * Cin, 1)
+    y = torch.empty((B, Cout) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    if y.numel() == 0:
+        return y
+    with torch.cuda.device(x.device):
+        wb = lib().vqb_conv1x1_workspace_bytes(Cin, Cout)
+        ws = _bytes(wb, x.device)
+        prof = PROFILE_CONV
+        if prof is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        check(lib().vqb_conv1x1_f32(_p(x), B, Cin, HW, _p(weight), _p(bias), Cout, _p(y), _p(ws), wb, int(algo),
+                                    _stream()), "vqb_conv1x1_f32")
+        if prof is not None:
+            ev1.record()
+            prof.append((ev0, ev1))
+        _count("conv", 2 if wb else 1)
+    return y
+
+
+@conv1x1.register_fake
+def _(x, weight, bias, algo=0):
+    return x.new_empty((x.shape[0], weight.shape[0]) + tuple(x.shape[2:]))
+
+
+def _conv1x1_setup(ctx, inputs, output):
+    x, weight, bias, algo = inputs
+    ctx.save_for_backward(x, weight)
+    ctx.has_bias = bias is not None
+    ctx.algo = algo
+
+
+def _conv1x1_bwd(ctx, gy):
+    x, weight = ctx.saved_tensors
+    w2 = weight.reshape(weight.shape[0], -1)
+    gx = gw = gb = None
+    gy = gy.contiguous()
+    if ctx.needs_input_grad[0]:
+        # dx = W^T . dy is the same 1x1 convolution with the transposed weight: this library's kernel
+        # (a forced tensor path only applies when the transposed shape qualifies as well)
+        cin_t, cout_t = int(w2.shape[0]), int(w2.shape[1])
+        algo_t = ctx.algo if (ctx.algo != 1 or (cin_t % 32 == 0 and cout_t % 16 == 0 and cout_t <= 256)) else 0
+        gx = conv1x1(gy, w2.t().contiguous(), None, algo_t)
+    if ctx.needs_input_grad[1]:
+        # dW[o, c] = sum over tokens dy[o, t] x[c, t]: a tokens-long reduction; plain library GEMM (torch)
+        B, Cout = gy.shape[0], gy.shape[1]
+        gw = torch.einsum("bot,bct->oc", gy.reshape(B, Cout, -1), x.reshape(B, x.shape[1], -1)).reshape(weight.shape)
+    if ctx.has_bias and ctx.needs_input_grad[2]:
+        gb = gy.reshape(gy.shape[0], gy.shape[1], -1).sum(dim=(0, 2))
+    return gx, gw, gb, None
+
+
+torch.library.register_autograd("vqb200::conv1x1", _conv1x1_bwd, setup_context=_conv1x1_setup)
 
 
 def fma_peak_tflops(packed: bool, iters: int = 4096, repeats: int = 5) -> float:

@@ -109,3 +109,23 @@ class VectorQuantizer(nn.Module):
 def usage_ratio_like_reference(usage: torch.Tensor) -> float:
     """(usage > 0).float().mean().item() -- quantizer.py:147, for host-side checks."""
     return (usage > 0).float().mean().item()
+
+
+class QuantConv1x1(nn.Conv2d):
+    """`pre_quant_conv` / `post_quant_conv` of the reference VQVAE (`nn.Conv2d(cin, cout, kernel_size=1)`,
+    vq_vae.py:74-79) on libvqb200: same constructor arguments, parameters and state_dict keys
+    (`weight [cout, cin, 1, 1]`, `bias [cout]`), so `VQVAE.pre_quant_conv = QuantConv1x1(zc, D)` loads
+    reference checkpoints strictly.  Forward and the input gradient run on the hand-written kernel
+    (3xTF32 tcgen05 when cin % 32 == 0, cout % 16 == 0, cout <= 256; CUDA cores otherwise); the weight
+    gradient is a library GEMM."""
+
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True, *, algo: int = 0):
+        super().__init__(in_channels, out_channels, kernel_size=1, bias=bias)
+        self.algo = algo
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 4:
+            raise RuntimeError(f"expected x of shape [B, C, H, W], got {tuple(x.shape)}")
+        if x.dtype != torch.float32:
+            x = x.float()
+        return ops.conv1x1(x, self.weight, self.bias, self.algo)
