@@ -137,6 +137,14 @@ VQB_API int vqb_pack_argmin_keys(const float* dmin, const int64_t* idx, int64_t 
 VQB_API int vqb_unpack_argmin_keys(const int64_t* keys, int64_t n, int64_t* idx_out, float* dmin_out,
                            vqb_stream_t stream);
 
+/* data-parallel statistics message (one fp32 all-reduce per step):
+ * flat = [ dE (n_dE) | scalars | hist mod 4096 | hist div 4096 ]; unpack scales dE by dE_scale
+ * (1/world reproduces DDP's gradient averaging) and rebuilds the int64 histogram exactly. */
+VQB_API int vqb_stats_pack(const float* dE, int64_t n_dE, const float* scalars, int n_scalars,
+                   const int64_t* hist, int n_hist, float* flat_out, vqb_stream_t stream);
+VQB_API int vqb_stats_unpack(const float* flat, int64_t n_dE, int n_scalars, int n_hist, float dE_scale,
+                     float* dE_out, float* scalars_out, int64_t* hist_out, vqb_stream_t stream);
+
 /* ---- compact index maps (next row N3: VQVAE.encode_to_indices / decode_from_indices,
  * vq_vae.py:162-190, cached like preprocess_latents.py:236-238 but 1-4 bytes per token) ----
  * vqb_index_bytes(K): 1 (K <= 256), 2 (K <= 65536) or 4.

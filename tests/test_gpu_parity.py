@@ -294,3 +294,25 @@ def test_conv1x1_matches_torch_fp32(B, Cin, Cout, H, W, algo):
     assert float((gerr / gbound.clamp_min(1e-30)).max()) < 2e-6
     assert torch.allclose(mine.weight.grad.cpu(), ref.weight.grad, rtol=1e-4, atol=1e-4 * float(ref.weight.grad.abs().max()))
     assert torch.allclose(mine.bias.grad.cpu(), ref.bias.grad, rtol=1e-4, atol=1e-4 * float(ref.bias.grad.abs().max()))
+
+
+@pytest.mark.gpu
+def test_stats_pack_unpack_device_matches_host_mirror():
+    """The CUDA pack/unpack of the data-parallel statistics message equals the host logic bit for bit."""
+    from vq_gan_b200 import distributed as vdist, ops
+    g = torch.Generator().manual_seed(5)
+    dE = torch.randn(300, 7, generator=g)
+    hist = torch.randint(0, 3_000_000_000, (300,), generator=g)
+    hist[0], hist[1] = 0, 4095
+    sc = torch.randn(3, generator=g)
+    want = vdist.pack_stats(dE, hist, sc)
+    got = ops.stats_pack(dE.cuda(), hist.cuda(), sc.cuda())
+    assert torch.equal(got.cpu(), want)
+    # as if summed over 4 ranks
+    summed = want * 4
+    a, b, c = vdist.unpack_stats(summed, dE.shape, 3, 300)
+    a2, b2, c2 = ops.stats_unpack(summed.cuda(), dE.shape, 3, 300, 0.25)
+    assert torch.equal(a2.cpu(), a * 0.25) and torch.equal(b2.cpu(), b) and torch.equal(c2.cpu(), c)
+    # dE only
+    a3, b3, c3 = ops.stats_unpack(ops.stats_pack(dE.cuda(), None, None), dE.shape, 0, 0, 1.0)
+    assert torch.equal(a3.cpu(), dE) and b3 is None and c3 is None

@@ -17,7 +17,7 @@ LIBDIR = os.path.join(PKG, "lib")
 OBJDIR = os.path.join(PKG, "build")
 LIB = os.path.join(LIBDIR, "libvqb200.so")
 SOURCES = ["vqb_api.cu", "vqb_prepare.cu", "vqb_search_lowd.cu", "vqb_search_fp32.cu",
-           "vqb_search_tc.cu", "vqb_search_tc16.cu", "vqb_search_tclow.cu", "vqb_tail.cu", "vqb_indexio.cu", "vqb_conv1x1.cu", "vqb_ubench.cu"]
+           "vqb_search_tc.cu", "vqb_search_tc16.cu", "vqb_search_tclow.cu", "vqb_tail.cu", "vqb_indexio.cu", "vqb_stats.cu", "vqb_conv1x1.cu", "vqb_ubench.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

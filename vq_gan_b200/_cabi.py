@@ -43,6 +43,8 @@ PROTOTYPES = {
                                    c_float, c_float, c_void_p, c_void_p]),
     "vqb_pack_argmin_keys": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "vqb_unpack_argmin_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "vqb_stats_pack": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "vqb_stats_unpack": (c_int, [c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "vqb_index_bytes": (c_int, [c_int]),
     "vqb_indices_narrow": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "vqb_indices_widen": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),

@@ -64,10 +64,18 @@ def allreduce_stats(dE: torch.Tensor, hist: Optional[torch.Tensor] = None,
     every rank normalises its loss by its local n; the histogram
     and scalars are always summed.  Exact for world sizes up to 4096."""
     world = dist.get_world_size(group)
-    flat = pack_stats(dE, hist, scalars)
+    n_s = 0 if scalars is None else scalars.numel()
+    n_h = 0 if hist is None else hist.numel()
+    if dE.is_cuda and dE.dtype == torch.float32:
+        # one libvqb200 launch each way instead of a dozen elementwise torch kernels
+        from . import ops
+        flat = ops.stats_pack(dE, hist, scalars)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        out_dE, out_scalars, out_hist = ops.stats_unpack(flat, dE.shape, n_s, n_h, 1.0 / world if average_dE else 1.0)
+        return out_dE, out_hist, out_scalars
+    flat = pack_stats(dE, hist, scalars)  # host-side mirror (gloo tests)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    out_dE, out_scalars, out_hist = unpack_stats(
-        flat, dE.shape, 0 if scalars is None else scalars.numel(), 0 if hist is None else hist.numel())
+    out_dE, out_scalars, out_hist = unpack_stats(flat, dE.shape, n_s, n_h)
     if average_dE:
         out_dE = out_dE / world
     return out_dE, out_hist, out_scalars

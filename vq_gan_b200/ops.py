@@ -364,6 +364,39 @@ def _(keys):
     return torch.empty_like(keys), keys.new_empty(keys.shape, dtype=torch.float32)
 
 
+def stats_pack(dE: Tensor, hist: Optional[Tensor], scalars: Optional[Tensor]) -> Tensor:
+    """One flat fp32 message [dE | scalars | hist mod 4096 | hist div 4096] (CUDA tensors, one launch)."""
+    _need_cuda_f32(dE, "dE")
+    dE = dE.contiguous()
+    n_s = 0 if scalars is None else scalars.numel()
+    n_h = 0 if hist is None else hist.numel()
+    if scalars is not None:
+        scalars = scalars.reshape(-1).float().contiguous()
+    if hist is not None:
+        hist = hist.reshape(-1).long().contiguous()
+    flat = torch.empty(dE.numel() + n_s + 2 * n_h, dtype=torch.float32, device=dE.device)
+    with torch.cuda.device(dE.device):
+        check(lib().vqb_stats_pack(_p(dE), dE.numel(), _p(scalars), n_s, _p(hist), n_h, _p(flat), _stream()),
+              "vqb_stats_pack")
+        _count("keys")
+    return flat
+
+
+def stats_unpack(flat: Tensor, dE_shape, n_scalars: int, n_hist: int, dE_scale: float):
+    """Inverse of stats_pack: (dE * dE_scale, scalars or None, int64 hist or None)."""
+    n_dE = 1
+    for d in dE_shape:
+        n_dE *= int(d)
+    dE = torch.empty(tuple(dE_shape), dtype=torch.float32, device=flat.device)
+    scalars = torch.empty(n_scalars, dtype=torch.float32, device=flat.device) if n_scalars else None
+    hist = torch.empty(n_hist, dtype=torch.int64, device=flat.device) if n_hist else None
+    with torch.cuda.device(flat.device):
+        check(lib().vqb_stats_unpack(_p(flat), n_dE, n_scalars, n_hist, float(dE_scale), _p(dE), _p(scalars), _p(hist),
+                                     _stream()), "vqb_stats_unpack")
+        _count("keys")
+    return dE, scalars, hist
+
+
 _NARROW_DTYPES = {1: torch.uint8, 2: torch.uint16, 4: torch.int32}
 
 
