@@ -316,3 +316,31 @@ def test_stats_pack_unpack_device_matches_host_mirror():
     # dE only
     a3, b3, c3 = ops.stats_unpack(ops.stats_pack(dE.cuda(), None, None), dE.shape, 0, 0, 1.0)
     assert torch.equal(a3.cpu(), dE) and b3 is None and c3 is None
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_matches_eager():
+    """CUDA-graph capture of forward + backward (launch-bound shapes) returns what the eager module returns."""
+    from vq_gan_b200 import VectorQuantizer
+    from vq_gan_b200.graphs import GraphedVectorQuantizer
+    for (K, D, B, H) in ((128, 256, 4, 32), (512, 4, 2, 16), (300, 64, 3, 24)):
+        torch.manual_seed(K)
+        vq = VectorQuantizer(K, D, 0.25, lazy_stats=True).cuda()
+        with torch.no_grad():
+            vq.embedding.weight.copy_(torch.randn(K, D))
+        gvq = GraphedVectorQuantizer(vq, torch.randn(B, D, H, H, device="cuda", requires_grad=True))
+        for trial in range(3):
+            z = torch.randn(B, D, H, H, device="cuda")
+            g = torch.randn(B, D, H, H, device="cuda")
+            outs = []
+            for mod in (vq, gvq):
+                zc = z.clone().requires_grad_(True)
+                vq.embedding.weight.grad = None
+                z_q, ld, idx = mod(zc)
+                torch.autograd.backward((z_q, ld["vq_loss"]), (g, torch.ones((), device="cuda")))
+                outs.append((z_q.detach().clone(), ld["vq_loss"].detach().clone(), ld["codebook_loss"].clone(),
+                             idx.clone(), zc.grad.clone(), vq.embedding.weight.grad.clone()))
+            e, r = outs
+            assert torch.equal(e[0], r[0]) and torch.equal(e[3], r[3]) and torch.equal(e[4], r[4])
+            assert torch.equal(e[1], r[1]) and torch.equal(e[2], r[2])
+            assert torch.allclose(e[5], r[5], rtol=1e-5, atol=1e-6 * float(e[5].abs().max()))

@@ -121,7 +121,12 @@ static int resolve_algo(int algo, int D, int64_t N = 0, int K = 0) {
         const bool large = (double)N * (double)K >= 268435456.0;  // 2^28 scores
         return (D >= 5 && large) ? VQB_ALGO_TCGEN05_TF32X3 : VQB_ALGO_LOWD_FMA;
     }
-    if (tc_eligible_dim(D)) return VQB_ALGO_TCGEN05_F16;  // single fp16 pass + exact re-score: 2.4x the bf16x3 kernel
+    if (tc_eligible_dim(D)) {
+        // below ~1 GFLOP the five-launch tensor pipeline is latency-bound (80 us floor): one fp32 tile kernel wins
+        // (reference default shape: 4096 tokens x 128 codes x 256 dims = 0.27 GFLOP)
+        if (N > 0 && (double)N * (double)K * (double)D < 536870912.0) return VQB_ALGO_FP32_TILE;
+        return VQB_ALGO_TCGEN05_F16;  // single fp16 pass + exact re-score: 2.4x the bf16x3 kernel
+    }
     return VQB_ALGO_FP32_TILE;
 }
 
