@@ -27,8 +27,10 @@ def algos_for(D):
     out = [0, 2]
     if D <= 16:
         out += [1, 5]
+    if 16 < D <= 256:
+        out.append(4)
     if D % 64 == 0 and 64 <= D <= 256:
-        out += [3, 4]
+        out.append(3)
     return out
 
 

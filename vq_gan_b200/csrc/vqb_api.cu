@@ -121,7 +121,7 @@ static int resolve_algo(int algo, int D, int64_t N = 0, int K = 0) {
         const bool large = (double)N * (double)K >= 268435456.0;  // 2^28 scores
         return (D >= 5 && large) ? VQB_ALGO_TCGEN05_TF32X3 : VQB_ALGO_LOWD_FMA;
     }
-    if (tc_eligible_dim(D)) {
+    if (tc16_eligible_dim(D)) {
         // below ~1 GFLOP the five-launch tensor pipeline is latency-bound (80 us floor): one fp32 tile kernel wins
         // (reference default shape: 4096 tokens x 128 codes x 256 dims = 0.27 GFLOP)
         if (N > 0 && (double)N * (double)K * (double)D < 536870912.0) return VQB_ALGO_FP32_TILE;
@@ -188,8 +188,8 @@ extern "C" int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, cons
             return launch_search_tc(z, B, D, HW, E, K, pack, idx_out, dmin_out, workspace, workspace_bytes,
                                     stats_out, s);
         case VQB_ALGO_TCGEN05_F16:
-            if (!tc_eligible_dim(D)) {
-                set_error("VQB_ALGO_TCGEN05_F16 needs D %% 64 == 0 and %d <= D <= %d, got %d", kTcMinD, kTcMaxD, D);
+            if (!tc16_eligible_dim(D)) {
+                set_error("VQB_ALGO_TCGEN05_F16 needs %d < D <= %d, got %d", kLowDMax, kTcMaxD, D);
                 return VQB_ERR_UNSUPPORTED;
             }
             return launch_search_tc16(z, B, D, HW, E, K, pack, idx_out, dmin_out, workspace, workspace_bytes,

@@ -39,7 +39,8 @@ int sm_count();  // cached per current device
 //            (h[2p], h[2p+1]) pairs by the low-D kernel.
 // pairs    : float[Kpad/2][2D]  (D <= 16)  e_d(2p), e_d(2p+1) interleaved per d
 // ehi, elo : bf16[Kpad][D]      (tensor path) E ~= ehi + elo, zero rows for k >= K
-// e16      : fp16[Kpad][D]      (single-pass tensor path) fp16(E * 2^se), zero rows for k >= K
+// e16      : fp16[Kpad][Dpad]   (single-pass tensor path, 16 < D <= 256) fp16(E * 2^se), zero rows for k >= K,
+//            zero columns for d >= D (Dpad = D rounded up to 64)
 constexpr int kPadCodes = 256;
 constexpr int kHeaderBytes = 256;
 constexpr int kLowDMax = 16;
@@ -49,14 +50,18 @@ constexpr int kTcMaxD = 256;
 __host__ __device__ inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
 __host__ __device__ inline size_t round_up_z(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
-__host__ __device__ inline bool tc_eligible_dim(int D) {
+__host__ __device__ inline bool tc_eligible_dim(int D) {  // bf16x3 kernel: whole 64-channel blocks only
     return D >= kTcMinD && D <= kTcMaxD && (D % 64) == 0;
 }
+// single-pass fp16 kernel: any 16 < D <= 256, the fp16 operand images are zero-padded to 64-channel blocks
+__host__ __device__ inline bool tc16_eligible_dim(int D) { return D > kLowDMax && D <= kTcMaxD; }
+__host__ __device__ inline int tc16_dpad(int D) { return round_up_i(D, 64); }
 
 struct PackLayout {
     int K, D, Kpad;
     size_t off_half_norm, off_pairs, off_ehi, off_elo, off_e16, off_half_norm_fin, off_img, total;
-    bool has_pairs, has_bf16;
+    bool has_pairs, has_bf16, has_e16;
+    int Dpad;  // row length of the fp16 image (D rounded up to 64)
 };
 
 // ---- tf32x3 operand images of the low-D tensor path (vqb_search_tclow.cu) -----------------
@@ -80,6 +85,8 @@ __host__ __device__ inline PackLayout pack_layout(int K, int D) {
     L.Kpad = round_up_i(K, kPadCodes);
     L.has_pairs = D <= kLowDMax;
     L.has_bf16 = tc_eligible_dim(D);
+    L.has_e16 = tc16_eligible_dim(D);
+    L.Dpad = tc16_dpad(D);
     size_t off = kHeaderBytes;
     L.off_half_norm = off;
     off = round_up_z(off + sizeof(float) * L.Kpad, 1024);
@@ -90,9 +97,9 @@ __host__ __device__ inline PackLayout pack_layout(int K, int D) {
     L.off_elo = off;
     if (L.has_bf16) off = round_up_z(off + 2 * (size_t)L.Kpad * D, 1024);
     L.off_e16 = off;
-    if (L.has_bf16) off = round_up_z(off + 2 * (size_t)L.Kpad * D, 1024);
+    if (L.has_e16) off = round_up_z(off + 2 * (size_t)L.Kpad * L.Dpad, 1024);
     L.off_half_norm_fin = off;  // half norms with a large FINITE pad (1e38) for the key-packing epilogue
-    if (L.has_bf16) off = round_up_z(off + sizeof(float) * L.Kpad, 1024);
+    if (L.has_e16) off = round_up_z(off + sizeof(float) * L.Kpad, 1024);
     L.off_img = off;  // tf32x3 codebook image (D <= 16)
     if (L.has_pairs) off = round_up_z(off + sizeof(float) * tclow_tile_floats(D) * (L.Kpad / kLowRows), 1024);
     L.total = off;

@@ -72,12 +72,16 @@ __global__ void __launch_bounds__(256) codebook_prepare_kernel(const float* __re
             const float rem = v - __bfloat162float(hi);
             ehi[(size_t)k * D + d] = hi;
             elo[(size_t)k * D + d] = __float2bfloat16_rn(rem);
+        }
+        if (L.has_e16) {
             const __half hv = __float2half_rn(ldexpf(v, se));
-            e16[(size_t)k * D + d] = hv;
+            e16[(size_t)k * L.Dpad + d] = hv;
             const float dv = v - ldexpf(__half2float(hv), -se);
             res = fmaf(dv, dv, res);
         }
     }
+    if (L.has_e16)  // zero padding up to whole 64-channel blocks
+        for (int d = D + lane; d < L.Dpad; d += 32) e16[(size_t)k * L.Dpad + d] = __float2half_rn(0.f);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
 #pragma unroll
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(256) codebook_prepare_kernel(const float* __re
     bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
         half_norm[k] = live ? 0.5f * sq : INFINITY;
-        if (L.has_bf16) {
+        if (L.has_e16) {
             const float h = 0.5f * sq;
             reinterpret_cast<float*>(pack + L.off_half_norm_fin)[k] = (live && h < 1e38f) ? h : 1e38f;
         }
@@ -137,7 +141,7 @@ int launch_codebook_prepare(const float* E, int K, int D, void* pack, cudaStream
     const PackLayout L = pack_layout(K, D);
     prepare_header_kernel<<<1, 32, 0, s>>>(reinterpret_cast<int*>(pack), K, D);
     VQB_LAUNCH_CHECK("prepare_header_kernel");
-    if (L.has_bf16) {
+    if (L.has_e16) {
         const size_t n = (size_t)K * D;
         size_t ab = (n + 255) / 256;
         if (ab > (size_t)sm_count() * 8) ab = (size_t)sm_count() * 8;

@@ -38,16 +38,14 @@ constexpr uint32_t kT16Idesc = (1u << 4)  // accumulator f32; A, B = f16 (format
 // pre-pass: z[B, D, HW] fp32 -> z16[N, D] fp16 scaled per token, 1/(s_i*se), |z_i|, |dz_i|
 // (one global read: the 32-token x D tile waits in shared memory while the scale is found)
 // ---------------------------------------------------------------------------
-constexpr int kSplitDimMax = 256;
-
-// NCH = D / 32 (2, 4, 6, 8): every loop below has a compile-time trip count, so the addresses are
+// NCH = padded D / 32 (2, 4, 6, 8): every loop below has a compile-time trip count, so the addresses are
 // immediates (the run-time-D version spent 3 of 4 issue slots on address arithmetic)
 template <int NCH>
 __global__ void __launch_bounds__(256)
-    split16_tokens_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const int* __restrict__ header,
+    split16_tokens_kernel(const float* __restrict__ z, int64_t N, int Dreal, int64_t HW, const int* __restrict__ header,
                           __half* __restrict__ z16, float* __restrict__ inv_scale, float* __restrict__ znorm,
                           float* __restrict__ zres) {
-    constexpr int D = 32 * NCH;
+    constexpr int D = 32 * NCH;  // padded row length (multiple of 64); channels >= Dreal are zeros
     __shared__ float tile[D][33];
     __shared__ float part_a[8][32];
     __shared__ float part_b[8][32];
@@ -61,11 +59,11 @@ __global__ void __launch_bounds__(256)
     bool finite = true;
     {
         const int64_t b = ok ? tok / HW : 0;
-        const float* zp = z + (b * D) * HW + (ok ? tok - b * HW : 0) + (int64_t)ty * HW;
+        const float* zp = z + (b * Dreal) * HW + (ok ? tok - b * HW : 0) + (int64_t)ty * HW;
         const int64_t step = 8 * HW;
 #pragma unroll
         for (int i = 0; i < D / 8; ++i) {
-            const float v = ok ? __ldg(zp) : 0.f;
+            const float v = (ok && ty + 8 * i < Dreal) ? __ldg(zp) : 0.f;
             zp += step;
             tile[ty + 8 * i][tx] = v;
             sq = fmaf(v, v, sq);
@@ -485,11 +483,11 @@ template <int NCH>
 __global__ void __launch_bounds__(256)
     rescore_groups_kernel(const float* __restrict__ z, const float* __restrict__ E, const float* __restrict__ half_norm,
                           const int32_t* __restrict__ group1, const int32_t* __restrict__ group2,
-                          const int32_t* __restrict__ group3, int64_t N, int64_t HW, int K,
+                          const int32_t* __restrict__ group3, int64_t N, int D, int64_t HW, int K,
                           int64_t* __restrict__ idx_out, float* __restrict__ dmin_out) {
-    constexpr int D = 32 * NCH;
+    constexpr int DT = 32 * NCH;  // D rounded up to 32; tile rows >= D are zeros
     // row stride 36 floats: the 4 tokens of a warp are one aligned 16-byte read, stores stay conflict-free
-    __shared__ __align__(16) float tile[D][36];
+    __shared__ __align__(16) float tile[DT][36];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t t0 = (int64_t)blockIdx.x * 32;
     {
@@ -499,8 +497,8 @@ __global__ void __launch_bounds__(256)
             const float* zp = z + (b * D) * HW + (tok - b * HW) + (int64_t)ty * HW;
             const int64_t step = 8 * HW;
 #pragma unroll
-            for (int i = 0; i < D / 8; ++i) {
-                tile[ty + 8 * i][tx] = __ldg(zp);
+            for (int i = 0; i < DT / 8; ++i) {
+                tile[ty + 8 * i][tx] = (ty + 8 * i < D) ? __ldg(zp) : 0.f;
                 zp += step;
             }
         }
@@ -529,8 +527,10 @@ __global__ void __launch_bounds__(256)
     for (int c = 0; c < NCH; ++c) {
         const float4 z4 = *reinterpret_cast<const float4*>(&tile[32 * c + lane][r0]);
         const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
+        if (32 * c + lane < D) {  // always true except in the last block of a D that is not a multiple of 32
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = fmaf(zv[j >> 2], __ldg(row[j] + 32 * c), acc[j]);
+            for (int j = 0; j < 16; ++j) acc[j] = fmaf(zv[j >> 2], __ldg(row[j] + 32 * c), acc[j]);
+        }
     }
     // transposed butterfly: afterwards lane L holds the full sum of accumulator (L >> 1) & 15
     {
@@ -648,7 +648,7 @@ static T16Workspace t16_workspace(int64_t N, int D) {
     T16Workspace w;
     size_t off = 0;
     w.off_z16 = off;
-    off = round_up_z(off + 2 * (size_t)N * D, 1024);
+    off = round_up_z(off + 2 * (size_t)N * tc16_dpad(D), 1024);
     w.off_inv = off;
     off = round_up_z(off + 4 * (size_t)N, 1024);
     w.off_znorm = off;
@@ -749,24 +749,25 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
     int32_t* counts = reinterpret_cast<int32_t*>(wsb + w.off_counts);
 
     VQB_CUDA_TRY(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), s));
+    const int Dpad = L.Dpad;
     {
         const unsigned blocks = (unsigned)((N + 31) / 32);
         const int* hdr = reinterpret_cast<const int*>(pk);
-        switch (D / 32) {
-            case 2: split16_tokens_kernel<2><<<blocks, 256, 0, s>>>(z, N, HW, hdr, z16, inv, znorm, zres); break;
-            case 4: split16_tokens_kernel<4><<<blocks, 256, 0, s>>>(z, N, HW, hdr, z16, inv, znorm, zres); break;
-            case 6: split16_tokens_kernel<6><<<blocks, 256, 0, s>>>(z, N, HW, hdr, z16, inv, znorm, zres); break;
-            default: split16_tokens_kernel<8><<<blocks, 256, 0, s>>>(z, N, HW, hdr, z16, inv, znorm, zres); break;
+        switch (Dpad / 32) {
+            case 2: split16_tokens_kernel<2><<<blocks, 256, 0, s>>>(z, N, D, HW, hdr, z16, inv, znorm, zres); break;
+            case 4: split16_tokens_kernel<4><<<blocks, 256, 0, s>>>(z, N, D, HW, hdr, z16, inv, znorm, zres); break;
+            case 6: split16_tokens_kernel<6><<<blocks, 256, 0, s>>>(z, N, D, HW, hdr, z16, inv, znorm, zres); break;
+            default: split16_tokens_kernel<8><<<blocks, 256, 0, s>>>(z, N, D, HW, hdr, z16, inv, znorm, zres); break;
         }
     }
     VQB_LAUNCH_CHECK("split16_tokens_kernel");
 
     // codebook maps: the box is the slice one CTA of the cluster fetches (256, 128 or 64 rows)
     CUtensorMap mz, me1, me2, me4;
-    if (int rc = make_tc_map(&mz, z16, (uint64_t)N, D, kTcBM, true)) return rc;
-    if (int rc = make_tc_map(&me1, pk + L.off_e16, (uint64_t)L.Kpad, D, kTcBN, true)) return rc;
-    if (int rc = make_tc_map(&me2, pk + L.off_e16, (uint64_t)L.Kpad, D, kTcBN / 2, true)) return rc;
-    if (int rc = make_tc_map(&me4, pk + L.off_e16, (uint64_t)L.Kpad, D, kTcBN / 4, true)) return rc;
+    if (int rc = make_tc_map(&mz, z16, (uint64_t)N, Dpad, kTcBM, true)) return rc;
+    if (int rc = make_tc_map(&me1, pk + L.off_e16, (uint64_t)L.Kpad, Dpad, kTcBN, true)) return rc;
+    if (int rc = make_tc_map(&me2, pk + L.off_e16, (uint64_t)L.Kpad, Dpad, kTcBN / 2, true)) return rc;
+    if (int rc = make_tc_map(&me4, pk + L.off_e16, (uint64_t)L.Kpad, Dpad, kTcBN / 4, true)) return rc;
 
     T16Params p;
     p.N = N;
@@ -785,26 +786,30 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
     p.full_list = reinterpret_cast<int32_t*>(wsb + w.off_full);
     p.full_count = counts + 0;
     int rc;
-    switch (D / kTcBK) {
+    switch (Dpad / kTcBK) {
         case 1: rc = launch_tc16_t<1>(mz, me1, me2, me4, p, s); break;
         case 2: rc = launch_tc16_t<2>(mz, me1, me2, me4, p, s); break;
         case 3: rc = launch_tc16_t<3>(mz, me1, me2, me4, p, s); break;
         case 4: rc = launch_tc16_t<4>(mz, me1, me2, me4, p, s); break;
         default:
-            set_error("fp16 tensor search supports D in {64,128,192,256}, got %d", D);
+            set_error("fp16 tensor search supports 16 < D <= 256, got %d", D);
             return VQB_ERR_UNSUPPORTED;
     }
     if (rc != VQB_OK) return rc;
     // exact fp32 choice among the 4 (or 8) certified candidates of every token
     {
         const unsigned blocks = (unsigned)((N + 31) / 32);
-#define VQB_RESCORE(nch)                                                                                              \
-    rescore_groups_kernel<nch><<<blocks, 256, 0, s>>>(z, E, p.half_norm, p.group1, p.group2, p.group3, N, HW, K, idx_out, \
+#define VQB_RESCORE(nch)                                                                                                 \
+    rescore_groups_kernel<nch><<<blocks, 256, 0, s>>>(z, E, p.half_norm, p.group1, p.group2, p.group3, N, D, HW, K, idx_out, \
                                                       dmin_out)
-        switch (D / 32) {
+        switch ((D + 31) / 32) {
+            case 1: VQB_RESCORE(1); break;
             case 2: VQB_RESCORE(2); break;
+            case 3: VQB_RESCORE(3); break;
             case 4: VQB_RESCORE(4); break;
+            case 5: VQB_RESCORE(5); break;
             case 6: VQB_RESCORE(6); break;
+            case 7: VQB_RESCORE(7); break;
             default: VQB_RESCORE(8); break;
         }
 #undef VQB_RESCORE
