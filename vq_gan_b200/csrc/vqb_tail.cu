@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kTailThreads)
 }
 
 // ---------------------------------------------------------------------------
-// D % 64 == 0: shared-memory transposed variants.  A CTA owns 32 consecutive tokens and up to
+// D % 32 == 0: shared-memory transposed variants.  A CTA owns 32 consecutive tokens and up to
 // 256 channels at a time: codebook rows are read as full 128-byte lines (lane = channel),
 // transposed through a conflict-free [channels][33] tile, and combined with z / g in the
 // token-major (lane = token) orientation in which z, z_q, dz are coalesced.  The dE scatter goes
@@ -356,8 +356,9 @@ __global__ void __launch_bounds__(256, DC <= 64 ? 4 : (DC <= 128 ? 3 : 2))
                     float* drow = dE + (size_t)tt.code[t] * D + d0 + 4 * l16;
 #pragma unroll
                     for (int c = 0; c < DC; c += 64)
-                        red_add_v4(drow + c, tile[c + 4 * l16 + 0][t], tile[c + 4 * l16 + 1][t], tile[c + 4 * l16 + 2][t],
-                                   tile[c + 4 * l16 + 3][t]);
+                        if (DC % 64 == 0 || c + 4 * l16 < DC)  // DC = 32: the upper eight lanes of the half-warp idle
+                            red_add_v4(drow + c, tile[c + 4 * l16 + 0][t], tile[c + 4 * l16 + 1][t],
+                                       tile[c + 4 * l16 + 2][t], tile[c + 4 * l16 + 3][t]);
                 }
             }
         }
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(256, DC <= 64 ? 4 : (DC <= 128 ? 3 : 2))
 static int tiled_pass_width(int D, int cap) {
     for (int dc = cap; dc >= 64; dc -= 64)
         if (D % dc == 0) return dc;
-    return 64;
+    return 32;  // callers guarantee D % 32 == 0
 }
 
 // ---------------------------------------------------------------------------
@@ -623,7 +624,7 @@ extern "C" int vqb_gather_loss_st_f32(const float* z, const float* E, const int6
     }
     const dim3 block(sh.tx, sh.slices);
     double* parts = static_cast<double*>(partials);
-    if (D % 64 == 0) {
+    if (D % 32 == 0) {
         const int64_t tb = (N + kTileTok - 1) / kTileTok;
 #define VQB_GATHER(dc) \
     gather_loss_st_tiled_kernel<dc><<<(unsigned)tb, 256, 0, s>>>(z, E, idx, N, D, HW, K, zq_out, parts, err_flag)
@@ -631,7 +632,8 @@ extern "C" int vqb_gather_loss_st_f32(const float* z, const float* E, const int6
             case 256: VQB_GATHER(256); break;
             case 192: VQB_GATHER(192); break;
             case 128: VQB_GATHER(128); break;
-            default: VQB_GATHER(64); break;
+            case 64: VQB_GATHER(64); break;
+            default: VQB_GATHER(32); break;
         }
 #undef VQB_GATHER
         VQB_LAUNCH_CHECK("gather_loss_st_tiled_kernel");
@@ -669,7 +671,7 @@ extern "C" int vqb_backward_f32(const float* z, const float* E, const int64_t* i
     const float norm = (float)(2.0 / ((double)N * D));
     unsigned long long* hist = reinterpret_cast<unsigned long long*>(hist_accum);
     const bool v4 = vec4_ok(D, E) && (!dE_accum || (reinterpret_cast<uintptr_t>(dE_accum) & 15u) == 0);
-    if (D % 64 == 0 && (!dE_accum || (reinterpret_cast<uintptr_t>(dE_accum) & 15u) == 0)) {
+    if (D % 32 == 0 && (!dE_accum || (reinterpret_cast<uintptr_t>(dE_accum) & 15u) == 0)) {
         const int64_t tb = (N + kTileTok - 1) / kTileTok;
 #define VQB_BWD(dc)                                                                                            \
     backward_tiled_kernel<dc><<<(unsigned)tb, 256, 0, s>>>(z, E, idx, g_zq, g_vq, beta, norm, N, D, HW, K, dz_out, \
@@ -678,7 +680,8 @@ extern "C" int vqb_backward_f32(const float* z, const float* E, const int64_t* i
             case 256: VQB_BWD(256); break;
             case 192: VQB_BWD(192); break;
             case 128: VQB_BWD(128); break;
-            default: VQB_BWD(64); break;
+            case 64: VQB_BWD(64); break;
+            default: VQB_BWD(32); break;
         }
 #undef VQB_BWD
         VQB_LAUNCH_CHECK("backward_tiled_kernel");
