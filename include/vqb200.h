@@ -62,9 +62,16 @@ VQB_API const char* vqb_last_error(void);
 VQB_API int vqb_device_query(int device, int* sm_count, int* cc_major, int* cc_minor,
                      size_t* smem_optin_bytes);
 
-/* launch-shape tuning knobs for experiments ("lowd_variant" = 0..4, "tc16_cluster" and
- * "tclow_cluster" = 1|2|4);
- * defaults are the shipped ones */
+/* Process-wide knobs for experiments; the defaults are the shipped configuration.
+ *   "lowd_variant"      0..4   launch shape of the CUDA-core low-D search (0 = 256 threads x 2 CTA/SM);
+ *                       16+n   n = 1: one CTA per SM (room for a co-running kernel), n = 0: default
+ *   "tc16_cluster"      1|2|4  cluster size (codebook-stage multicast) of the fp16 tensor search
+ *   "tclow_cluster"     1|2|4  same for the low-D tensor search; 16+mask skips stages for bisection
+ *                              (1 tensor kernel, 2 chunk re-score, 4 exact list search) -- results are
+ *                              then wrong by design
+ *   "fwd_pass_channels" / "bwd_pass_channels"  64|128|192|256  channels per pass of the tiled tail kernels
+ *   "conv_debug"        0..15  bit mask for the 1x1 convolution: 1 no activation loads, 2 no stores,
+ *                              4 one MMA in three (timing experiments only) */
 VQB_API int vqb_tune(const char* key, int value);
 
 /* ---- codebook pre-pass -------------------------------------------------

@@ -346,3 +346,39 @@ def test_cuda_graph_replay_matches_eager():
             assert torch.equal(e[0], r[0]) and torch.equal(e[3], r[3]) and torch.equal(e[4], r[4])
             assert torch.equal(e[1], r[1]) and torch.equal(e[2], r[2])
             assert torch.allclose(e[5], r[5], rtol=1e-5, atol=1e-6 * float(e[5].abs().max()))
+
+
+@pytest.mark.gpu
+def test_ema_quantizer_module_matches_oracle_update():
+    """Extension (parity unpinned): EMAVectorQuantizer = reference forward outputs + VQ-VAE EMA codebook update."""
+    from vq_gan_b200 import EMAVectorQuantizer
+    c = make_case("small_d8")
+    K, D = c["E"].shape
+    vq = EMAVectorQuantizer(K, D, 0.25, decay=0.9, eps=1e-5).cuda()
+    with torch.no_grad():
+        vq.embedding.weight.copy_(c["E"])
+        vq.embed_sum.copy_(c["E"])
+        vq.cluster_size.fill_(1.0)
+    z = c["z"].cuda().requires_grad_(True)
+    z_q, ld, idx = vq(z)
+    ld["vq_loss"].backward()
+    rows = orc.tokens_of(c["z"])
+    got_idx = idx.reshape(-1).cpu()
+    fo = orc.forward(c["z"], c["E"], 0.25, idx=got_idx)
+    assert torch.equal(z_q.detach().cpu(), fo["z_q"])
+    mse = float(fo["mse"]) if "mse" in fo else ld["codebook_loss"]
+    np.testing.assert_allclose(ld["vq_loss"].item(), 0.25 * ld["codebook_loss"], rtol=1e-5)
+    # gradient: beta * (2/n) (z - e), nothing to the codebook
+    e = c["E"][got_idx]
+    want_dz = 0.25 * 2.0 / c["z"].numel() * (rows - e)
+    np.testing.assert_allclose(orc.tokens_of(z.grad.cpu()).numpy(), want_dz.numpy(), rtol=1e-5, atol=1e-9)
+    assert vq.embedding.weight.grad is None
+    want = orc.ema_update(c["E"], torch.ones(K), c["E"].clone(), rows, got_idx, 0.9, 1e-5)
+    np.testing.assert_allclose(vq.embedding.weight.detach().cpu().numpy(), want[0].numpy(), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(vq.cluster_size.cpu().numpy(), want[1].numpy(), rtol=1e-6)
+    np.testing.assert_allclose(vq.embed_sum.cpu().numpy(), want[2].numpy(), rtol=1e-5, atol=1e-6)
+    # eval mode leaves the codebook alone
+    vq.eval()
+    before = vq.embedding.weight.detach().clone()
+    vq(c["z"].cuda())
+    assert torch.equal(before, vq.embedding.weight.detach())

@@ -52,7 +52,7 @@ struct ConvParams {
     const float* bias;  // nullable
     int64_t N, HW;
     int Cin, Cout;
-    int dbg;  // experiments: 1 no activation loads, 2 no output stores, 4 one MMA in twelve, 8 no weight TMA after the first two
+    int dbg;  // experiments (vqb_tune "conv_debug"): 1 no activation loads, 2 no output stores, 4 one MMA in three
 };
 
 template <int CL>

@@ -129,3 +129,52 @@ class QuantConv1x1(nn.Conv2d):
         if x.dtype != torch.float32:
             x = x.float()
         return ops.conv1x1(x, self.weight, self.bias, self.algo)
+
+
+class EMAVectorQuantizer(VectorQuantizer):
+    """Extension (no reference code; semantics of the VQ-VAE paper, appendix A.1 -- PARITY UNPINNED):
+    the codebook is updated by exponential moving averages of the per-code token counts and sums instead
+    of by its gradient.  Forward outputs keep the reference contract; `vq_loss` is the commitment term
+    beta * mse(z, sg(e)) only and `embedding.weight` receives no gradient.  In training mode every forward
+    runs `vqb_code_sums_f32` + `vqb_ema_update_f32`; under torch.distributed the counts and sums are
+    summed over the ranks first (one all-reduce), so every replica applies the same update.
+
+    `cluster_size` / `embed_sum` are persistent buffers (extra state_dict keys: load reference checkpoints
+    with strict=False)."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, commitment_cost: float = 0.25, *,
+                 decay: float = 0.99, eps: float = 1e-5, **kw):
+        super().__init__(num_embeddings, embedding_dim, commitment_cost, **kw)
+        self.decay, self.eps = decay, eps
+        self.embedding.weight.requires_grad_(False)
+        self.register_buffer("cluster_size", torch.zeros(num_embeddings))
+        self.register_buffer("embed_sum", self.embedding.weight.detach().clone())
+
+    def forward(self, z: torch.Tensor):
+        if z.dtype != torch.float32:
+            z = z.float()
+        # training mode updates the codebook in place below: the backward pass must see the codebook this
+        # forward searched, so it gets a snapshot (K*D*4 bytes, negligible next to the latents)
+        w = self.embedding.weight.detach()
+        if self.training:
+            w = w.clone()
+        z_q, vq_loss, mse, indices, stats = ops.quantize(z, w, float(self.commitment_cost), self.algo)
+        self.last_search_stats = stats
+        # ops.quantize returns vq_loss = (1 + beta) * mse whose gradient w.r.t. z is (2/n)(z - e) (weight 1, the
+        # reference's "codebook_loss" branch).  The EMA variant keeps only beta * mse(z, sg(e)):
+        #   value    beta * (1 + beta) * mse - beta^2 * mse = beta * mse
+        #   gradient beta * (2/n)(z - e)
+        beta = float(self.commitment_cost)
+        commit = beta * vq_loss - (beta * beta) * mse.detach()
+        if self.training:
+            with torch.no_grad():
+                counts, sums = ops.code_sums(z.detach(), indices, self.num_embeddings)
+                if torch.distributed.is_available() and torch.distributed.is_initialized() \
+                        and torch.distributed.get_world_size() > 1:
+                    flat = torch.cat([counts, sums.reshape(-1)])
+                    torch.distributed.all_reduce(flat)
+                    counts, sums = flat[:self.num_embeddings], flat[self.num_embeddings:].reshape(sums.shape)
+                ops.ema_update(self.embedding.weight.data, self.cluster_size, self.embed_sum, counts.contiguous(),
+                               sums.contiguous(), float(self.decay), float(self.eps))
+        m = mse.detach() if self.lazy_stats else mse.item()
+        return z_q, {"vq_loss": commit, "codebook_loss": m, "commitment_loss": m}, indices
