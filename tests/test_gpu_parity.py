@@ -382,3 +382,19 @@ def test_ema_quantizer_module_matches_oracle_update():
     before = vq.embedding.weight.detach().clone()
     vq(c["z"].cuda())
     assert torch.equal(before, vq.embedding.weight.detach())
+
+
+@pytest.mark.gpu
+def test_conv1x1_persistent_edge_tiles():
+    """1x1 conv tensor path: one more 128-token tile than SMs (lone CTA in the second round, its cluster
+    partner pads) and a ragged last tile."""
+    from vq_gan_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for B, HW in ((149, 128), (297, 64), (1, 19000)):
+        x = torch.randn(B, 64, HW, generator=g).cuda()
+        w = (torch.randn(48, 64, generator=g) / 8).cuda()
+        b = torch.randn(48, generator=g).cuda()
+        y = ops.conv1x1(x, w, b, 1)
+        ref = torch.einsum("oc,bct->bot", w.double(), x.double()) + b.double().view(1, -1, 1)
+        bound = torch.einsum("oc,bct->bot", w.abs().double(), x.abs().double()) + b.abs().double().view(1, -1, 1)
+        assert float(((y.double() - ref).abs() / bound).max()) < 2e-6

@@ -27,6 +27,10 @@ def _cases():
         D = int(rng.choice([17, 24, 33, 48, 100, 200, 255, 320]))
         out.append((D, int(rng.choice([5, 200, 1500])), int(rng.integers(1, 4)), int(rng.choice([1, 37, 256])),
                     int(rng.integers(0, 1 << 30))))
+    # persistent-kernel edge cases: one more tile than SMs (second round with a lone CTA whose cluster
+    # partner only pads), ragged last tile, exactly one full wave
+    out += [(64, 300, 149, 128, 11), (4, 300, 149, 128, 12), (8, 257, 149, 128, 13), (256, 256, 297, 64, 14),
+            (128, 130, 148, 128, 15), (16, 1000, 2, 9500, 16), (32, 700, 3, 6400, 17)]
     return out
 
 
