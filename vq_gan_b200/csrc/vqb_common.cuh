@@ -146,7 +146,7 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 int launch_codebook_prepare(const float* E, int K, int D, void* pack, cudaStream_t s);
 int launch_search_lowd(const float* z, int64_t B, int D, int64_t HW, int K, const void* pack,
                        int64_t* idx_out, float* dmin_out, cudaStream_t s);
-size_t search_fp32_workspace_bytes(int64_t n_rows);
+size_t search_fp32_workspace_bytes(int64_t n_rows, int D = 0);
 int launch_search_fp32(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                        const void* pack, const int32_t* token_list, const int32_t* list_count,
                        int64_t max_list, void* keys_ws, size_t keys_bytes, int64_t* idx_out,

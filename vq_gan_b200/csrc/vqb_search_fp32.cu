@@ -35,8 +35,24 @@ __device__ __forceinline__ void key_unpack(unsigned long long key, float& d, int
     d = __int_as_float(bits);
 }
 
+constexpr int kFtCompactCap = 4096;  // flagged tokens staged dim-major ([D][cap]) so every code split reads them coalesced
+
+// list mode pre-pass: zc[d][r] = z[token list[r]][d] for r < count (skipped when the list is longer than the buffer)
+__global__ void __launch_bounds__(256)
+    gather_list_rows_kernel(const float* __restrict__ z, int D, int64_t HW, const int32_t* __restrict__ token_list,
+                            const int32_t* __restrict__ list_count, float* __restrict__ zc) {
+    const int count = *list_count;
+    if (count > kFtCompactCap) return;
+    const int r = blockIdx.x * 32 + (threadIdx.x & 31);
+    if (r >= count) return;
+    const int64_t t = token_list[r];
+    const int64_t b = t / HW;
+    const float* zp = z + (b * D) * HW + (t - b * HW);
+    for (int d = threadIdx.x >> 5; d < D; d += 8) zc[(size_t)d * kFtCompactCap + r] = __ldg(zp + (int64_t)d * HW);
+}
+
 __global__ void __launch_bounds__(kFtThreads, 2)
-    search_fp32_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW,
+    search_fp32_kernel(const float* __restrict__ z, int64_t N, int D, int64_t HW, const float* __restrict__ zc,
                        const float* __restrict__ E, int K, const unsigned char* __restrict__ pack,
                        PackLayout L, const int32_t* __restrict__ token_list,
                        const int32_t* __restrict__ list_count, int splits, int codes_per_split,
@@ -54,6 +70,11 @@ __global__ void __launch_bounds__(kFtThreads, 2)
     const int64_t n_items = n_tiles * splits;
     const float* half_norm = reinterpret_cast<const float*>(pack + L.off_half_norm);
     const int first_nan = reinterpret_cast<const int*>(pack)[0];
+    // a short list was gathered into zc (dim-major, row = list position): read that instead of the
+    // scattered tokens (which cost a 32-byte sector per 4-byte value, once per code split)
+    const bool compact = token_list != nullptr && zc != nullptr && count <= kFtCompactCap;
+    const float* zsrc = compact ? zc : z;
+    const int64_t zstride = compact ? (int64_t)kFtCompactCap : HW;
 
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int64_t tile = item / splits;
@@ -71,7 +92,7 @@ __global__ void __launch_bounds__(kFtThreads, 2)
             tok_id[tid] = t;
             if (t >= 0) {
                 const int64_t b = t / HW;
-                tok_off[tid] = (b * D) * HW + (t - b * HW);
+                tok_off[tid] = compact ? r : (b * D) * HW + (t - b * HW);
             } else {
                 tok_off[tid] = -1;
             }
@@ -100,7 +121,7 @@ __global__ void __launch_bounds__(kFtThreads, 2)
                     const int kk = e / kFtTokens, mm = e % kFtTokens;
                     const int64_t off = tok_off[mm];
                     float v = 0.f;
-                    if (off >= 0 && k0 + kk < D) v = __ldg(z + off + (int64_t)(k0 + kk) * HW);
+                    if (off >= 0 && k0 + kk < D) v = __ldg(zsrc + off + (int64_t)(k0 + kk) * zstride);
                     As[kk][mm] = v;
                 }
 #pragma unroll
@@ -194,7 +215,10 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-size_t search_fp32_workspace_bytes(int64_t n_rows) { return 8 * (size_t)n_rows + 1024; }
+// 8 bytes of key per row, then (D > 0) the compact buffer of the list mode
+size_t search_fp32_workspace_bytes(int64_t n_rows, int D) {
+    return round_up_z(8 * (size_t)n_rows + 1024, 1024) + (D > 0 ? sizeof(float) * (size_t)kFtCompactCap * D : 0);
+}
 
 // keys_ws: scratch of search_fp32_workspace_bytes(rows) bytes, needed when the codebook is split
 int launch_search_fp32(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
@@ -219,7 +243,13 @@ int launch_search_fp32(const float* z, int64_t B, int D, int64_t HW, const float
         splits = (int)(want < code_tiles ? want : code_tiles);
     }
     if (splits < 1) splits = 1;
-    if (splits > 1 && (keys_ws == nullptr || keys_bytes < search_fp32_workspace_bytes(rows))) splits = 1;
+    if (splits > 1 && (keys_ws == nullptr || keys_bytes < search_fp32_workspace_bytes(rows, 0))) splits = 1;
+    float* zc = nullptr;
+    if (token_list && keys_ws && keys_bytes >= search_fp32_workspace_bytes(rows, D)) {
+        zc = reinterpret_cast<float*>(static_cast<unsigned char*>(keys_ws) + round_up_z(8 * (size_t)rows + 1024, 1024));
+        gather_list_rows_kernel<<<kFtCompactCap / 32, 256, 0, s>>>(z, D, HW, token_list, list_count, zc);
+        VQB_LAUNCH_CHECK("gather_list_rows_kernel");
+    }
     const int tiles_per_split = (code_tiles + splits - 1) / splits;
     const int codes_per_split = tiles_per_split * kFtCodes;
     splits = (code_tiles + tiles_per_split - 1) / tiles_per_split;
@@ -232,7 +262,7 @@ int launch_search_fp32(const float* z, int64_t B, int D, int64_t HW, const float
     int64_t items = tiles * splits;
     const int64_t cap = (int64_t)sms * 2 * (token_list ? 1 : 64);  // persistent for lists
     const unsigned grid = (unsigned)(items < cap ? items : cap);
-    search_fp32_kernel<<<grid, kFtThreads, 0, s>>>(z, N, D, HW, E, K, static_cast<const unsigned char*>(pack),
+    search_fp32_kernel<<<grid, kFtThreads, 0, s>>>(z, N, D, HW, zc, E, K, static_cast<const unsigned char*>(pack),
                                                    L, token_list, list_count, splits, codes_per_split, keys,
                                                    idx_out, dmin_out);
     VQB_LAUNCH_CHECK("search_fp32_kernel");

@@ -350,7 +350,7 @@ static TcWorkspace tc_workspace(int64_t N, int D) {
     w.off_count = off;
     off += 1024;
     w.off_keys = off;
-    w.keys_bytes = search_fp32_workspace_bytes(N);
+    w.keys_bytes = search_fp32_workspace_bytes(N, D);
     off = round_up_z(off + w.keys_bytes, 1024);
     w.total = off;
     return w;
