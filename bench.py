@@ -287,7 +287,8 @@ def run_conv(args, world, rank, local_rank, device, B, Cin, H, W, Cout, desc, pe
                        "l2": "2 rotating input sets (2147 MB) > 126 MB L2"},
             "roofline": {"bound": "hbm", "kernel": "conv1x1_tc_kernel", "achieved": nbytes / (k_ms * 1e-3) / 1e9,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / (k_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                         "traffic": None, "kernel_ms": k_ms, "algorithmic_bytes_per_launch": nbytes,
+                         "traffic": load_traffic("conv1x1_tc_kernel", "n1"), "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": nbytes,
                          "tensor_tflops_algorithmic": flops / (k_ms * 1e-3) / 1e12, "executed_flops_factor": 3,
                          "tensor_frac_executed": 3 * flops / (k_ms * 1e-3) / 1e12 / (peaks["bf16_tflops_sustained"] / 2)},
             "e2e": {"value": tokens * world * e2e_steps / (e2e_ms * 1e-3), "unit": "tokens/s",
