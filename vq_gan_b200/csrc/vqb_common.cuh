@@ -35,6 +35,12 @@ int sm_count();  // cached per current device
 // header (int32[64]): [0] first NaN code (K if none) [1] K [2] D [4] float bits of max 0.5|e|^2
 //                      [5] fp16 scale exponent se (e16 = fp16(E * 2^se)) [6] float bits of max|E| [7] bits of max |e - fp16(e)|
 //                      [8] bits of max_k |e_k - eh_k - el_k| and [9] bits of max_k |el_k| (tf32x3 image, D <= 16)
+//                      residual bounds as a function of the code norm n = |e_k| (valid for EVERY code by construction:
+//                      rho = max relative residual over codes with n >= theta, a = max absolute residual below theta,
+//                      theta = 2^-12 max|E|):  [10],[11] fp16 image: |e - e16| <= rho16 n + a16;
+//                      [12],[13] tf32x3 residual |r_e| <= rho_r n + a_r;  [14],[15] low part |el| <= rho_l n + a_l
+// gmax     : float[Kpad/4]   max code norm per 4-code group  (fp16 tensor path, 16 < D <= 256)
+// cmax     : float[Kpad/32]  max code norm per 32-code chunk (low-D tensor path, D <= 16)
 // half_norm: float[Kpad]  0.5|e_k|^2, +inf for k >= K.  Read as consecutive
 //            (h[2p], h[2p+1]) pairs by the low-D kernel.
 // pairs    : float[Kpad/2][2D]  (D <= 16)  e_d(2p), e_d(2p+1) interleaved per d
@@ -59,7 +65,7 @@ __host__ __device__ inline int tc16_dpad(int D) { return round_up_i(D, 64); }
 
 struct PackLayout {
     int K, D, Kpad;
-    size_t off_half_norm, off_pairs, off_ehi, off_elo, off_e16, off_half_norm_fin, off_img, total;
+    size_t off_half_norm, off_pairs, off_ehi, off_elo, off_e16, off_half_norm_fin, off_img, off_gmax, off_cmax, total;
     bool has_pairs, has_bf16, has_e16;
     int Dpad;  // row length of the fp16 image (D rounded up to 64)
 };
@@ -102,6 +108,10 @@ __host__ __device__ inline PackLayout pack_layout(int K, int D) {
     if (L.has_e16) off = round_up_z(off + sizeof(float) * L.Kpad, 1024);
     L.off_img = off;  // tf32x3 codebook image (D <= 16)
     if (L.has_pairs) off = round_up_z(off + sizeof(float) * tclow_tile_floats(D) * (L.Kpad / kLowRows), 1024);
+    L.off_gmax = off;
+    if (L.has_e16) off = round_up_z(off + sizeof(float) * (L.Kpad / 4), 1024);
+    L.off_cmax = off;
+    if (L.has_pairs) off = round_up_z(off + sizeof(float) * (L.Kpad / 32), 1024);
     L.total = off;
     return L;
 }

@@ -17,6 +17,7 @@ __global__ void prepare_header_kernel(int* header, int K, int D) {
         header[7] = 0;  // bits of max_k |e_k - fp16 image of e_k| (residual of the single-pass tensor path)
         header[8] = 0;  // bits of max_k |e_k - eh_k - el_k| (tf32x3 image)
         header[9] = 0;  // bits of max_k |el_k|
+        for (int i = 10; i < 16; ++i) header[i] = 0;  // norm-dependent residual bounds (vqb_common.cuh)
     }
 }
 
@@ -96,6 +97,18 @@ __global__ void __launch_bounds__(256) codebook_prepare_kernel(const float* __re
         if (live && (bad || sq != sq)) atomicMin(&header[0], k);
         if (live && sq == sq) atomicMax(&header[4], __float_as_int(0.5f * sq));
         if (live && res == res && res > 0.f) atomicMax(&header[7], __float_as_int(sqrtf(res)));
+        if (L.has_e16 && live && sq == sq && sq < INFINITY) {
+            const float n = sqrtf(sq);
+            atomicMax(reinterpret_cast<int*>(pack + L.off_gmax) + (k >> 2), __float_as_int(n));
+            if (res == res && res > 0.f) {
+                const float theta = __int_as_float(header[6]) * (1.f / 4096.f);
+                const float r = sqrtf(res);
+                if (n >= theta && n > 0.f)
+                    atomicMax(&header[10], __float_as_int(r / n * 1.0000002f));  // rounded up
+                else
+                    atomicMax(&header[11], __float_as_int(r));
+            }
+        }
     }
 }
 
@@ -135,6 +148,16 @@ __global__ void __launch_bounds__(128) codebook_image_kernel(const float* __rest
     for (int sl = 3 * D + 3; sl < slots; ++sl) img[tclow_slot_offset(r, sl)] = 0.f;
     if (live && res == res && res > 0.f && res < INFINITY) atomicMax(&header[8], __float_as_int(sqrtf(res)));
     if (live && lo2 == lo2 && lo2 > 0.f && lo2 < INFINITY) atomicMax(&header[9], __float_as_int(sqrtf(lo2)));
+    if (live && h == h && h < INFINITY) {
+        const float n = sqrtf(2.f * h);
+        atomicMax(reinterpret_cast<int*>(pack + L.off_cmax) + (k >> 5), __float_as_int(n));
+        // theta from the half-norm maximum is not known yet (same kernel): max|E| is not computed for D <= 16,
+        // so classify against the code's own scale: relative bound for every code with n > 0
+        if (n > 0.f) {
+            if (res == res && res < INFINITY) atomicMax(&header[12], __float_as_int(sqrtf(res) / n * 1.0000002f));
+            if (lo2 == lo2 && lo2 < INFINITY) atomicMax(&header[14], __float_as_int(sqrtf(lo2) / n * 1.0000002f));
+        }
+    }
 }
 
 int launch_codebook_prepare(const float* E, int K, int D, void* pack, cudaStream_t s) {
@@ -148,6 +171,10 @@ int launch_codebook_prepare(const float* E, int K, int D, void* pack, cudaStream
         codebook_absmax_kernel<<<(unsigned)ab, 256, 0, s>>>(E, n, reinterpret_cast<int*>(pack));
         VQB_LAUNCH_CHECK("codebook_absmax_kernel");
     }
+    if (L.has_e16)
+        VQB_CUDA_TRY(cudaMemsetAsync(static_cast<unsigned char*>(pack) + L.off_gmax, 0, sizeof(float) * (L.Kpad / 4), s));
+    if (L.has_pairs)
+        VQB_CUDA_TRY(cudaMemsetAsync(static_cast<unsigned char*>(pack) + L.off_cmax, 0, sizeof(float) * (L.Kpad / 32), s));
     const int warps = 8;
     const int blocks = (L.Kpad + warps - 1) / warps;
     codebook_prepare_kernel<<<blocks, warps * 32, 0, s>>>(E, K, D, static_cast<unsigned char*>(pack), L);

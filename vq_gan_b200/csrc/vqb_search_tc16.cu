@@ -137,6 +137,7 @@ struct T16Params {
     const float* half_norm;      // exact, +inf padded (re-score kernels)
     const float* half_norm_fin;  // finite padding (epilogue keys must never be NaN)
     const int* header;
+    const float* gmax;       // [Kpad/4] max code norm per 4-code group
     const float* znorm;
     const float* zres;       // |z_i - fp16 image of z_i|
     const float* inv_scale;
@@ -319,7 +320,8 @@ __global__ void __launch_bounds__(kT16Threads, 1)
         const int first_nan = p.header[0];
         const float h_max = __int_as_float(p.header[4]);
         const float e_max = sqrtf(2.f * h_max);
-        const float de_max = __int_as_float(p.header[7]);  // max_k |e_k - fp16 image of e_k|
+        // |e_k - fp16 image of e_k| <= rho16 |e_k| + a16 for every code (measured by the prepare kernel)
+        const float rho16 = __int_as_float(p.header[10]), a16 = __int_as_float(p.header[11]);
         const int row_in_tile = q * 32 + lane;
         const int epi_tid = threadIdx.x - 128;  // 0..255
         const int n_super = (n_n_tiles + 3) / 4;
@@ -433,12 +435,25 @@ __global__ void __launch_bounds__(kT16Threads, 1)
                 top4_insert(m, x[1], __float_as_int(x[5]));
                 top4_insert(m, x[2], __float_as_int(x[6]));
                 if (x[3] < m.v4) m.v4 = x[3];
-                // eps_i: Cauchy-Schwarz on the measured fp16 residuals + fp32 accumulation (2^-15
-                // relative, covers both this kernel's and the re-score's sums) + the 8 masked bits
+                // Error of the approximate score of a code of norm n (Cauchy-Schwarz on the MEASURED fp16
+                // residuals; fp32 accumulation 2^-15 relative, covering this kernel's and the re-score's sums;
+                // the 8 masked mantissa bits are 2^-15 of the score, |score| <= n^2/2 + |z| n):
+                //   eps(n) = (|dz| + (|z| + |dz|) rho16 + 2^-15 |z|) n + (|z| + |dz|) a16 + 2^-14 (n^2/2 + |z| n)
+                // The approximate winner k1 sits in group i1 (norm <= n1): exact_best <= U = m1 + eps(n1).
+                // A code of norm n scores at least n^2/2 - |z| n exactly, so codes with n > n0 =
+                // |z| + sqrt(|z|^2 + 2U) cannot win whatever their approximate score; every other code has
+                // error <= eps(n0).  Hence a code outside the kept groups is excluded once its group minimum
+                // exceeds m1 by tau = eps(min(n0, max|e|)) + eps(n1) -- the threshold follows the norm of
+                // the WINNER, not the largest norm in the codebook (one outlier code no longer inflates it).
                 const float zn = p.znorm[row], zr = p.zres[row];
-                const float eps = zr * e_max + (zn + zr) * de_max + (1.f / 32768.f) * zn * e_max +
-                                  (1.f / 16384.f) * (h_max + zn * e_max);
-                const float tau = 2.f * eps;
+                const float alpha = zr + (zn + zr) * rho16 + (1.f / 32768.f) * zn;
+                const float beta0 = (zn + zr) * a16;
+                const float n1 = fminf(__ldg(p.gmax + m.i1), e_max);
+                const float eps1 = alpha * n1 + beta0 + (1.f / 16384.f) * (0.5f * n1 * n1 + zn * n1);
+                const float U = m.v1 + eps1;
+                const float n0 = fminf(zn + sqrtf(fmaxf(zn * zn + 2.f * U, 0.f)), e_max);
+                const float eps0 = alpha * n0 + beta0 + (1.f / 16384.f) * (0.5f * n0 * n0 + zn * n0);
+                const float tau = 1.0001f * (eps0 + eps1);
                 const bool only1 = (m.v2 - m.v1) > tau;  // every candidate is in group 1
                 const bool only2 = (m.v3 - m.v1) > tau;  // ... in groups 1-2
                 const bool only3 = (m.v4 - m.v1) > tau;  // ... in groups 1-3
@@ -786,6 +801,7 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
     p.half_norm = reinterpret_cast<const float*>(pk + L.off_half_norm);
     p.half_norm_fin = reinterpret_cast<const float*>(pk + L.off_half_norm_fin);
     p.header = reinterpret_cast<const int*>(pk);
+    p.gmax = reinterpret_cast<const float*>(pk + L.off_gmax);
     p.znorm = znorm;
     p.zres = zres;
     p.inv_scale = inv;

@@ -76,7 +76,7 @@ __device__ __forceinline__ void bulk_load_mc(void* dst, const void* src, uint32_
 template <int D>
 __global__ void __launch_bounds__(128)
     split_tf32_tokens_kernel(const float* __restrict__ z, int64_t N, int64_t HW, const int* __restrict__ header,
-                             float* __restrict__ img, float* __restrict__ tau) {
+                             float* __restrict__ img, float4* __restrict__ tok_norms) {
     constexpr int kSlots = 8 * ((3 * D + 3 + 7) / 8);
     const int64_t tok = (int64_t)blockIdx.x * 128 + threadIdx.x;  // block = one 128-row tile
     const bool ok = tok < N;
@@ -107,18 +107,9 @@ __global__ void __launch_bounds__(128)
     for (int c = 0; c < kSlots / 4; ++c)  // one 16-byte chunk per store, consecutive rows are adjacent
         *reinterpret_cast<float4*>(tile + c * (kLowRows * 4) + (r >> 3) * 32 + (r & 7) * 4) =
             make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-    if (ok) {
-        const float h_max = __int_as_float(header[4]);
-        const float e_max = sqrtf(2.f * h_max);
-        const float re_max = __int_as_float(header[8]), el_max = __int_as_float(header[9]);
-        const float zn = sqrtf(zz);
-        // fp32 accumulation of <= 8*steps exact products inside the tensor core: 2^-18 relative to
-        // the magnitude of the terms; 2^-20 covers the three-piece half norm and this estimate itself
-        const float mag = zn * e_max + h_max;
-        const float eps = sqrtf(res) * e_max + zn * re_max + sqrtf(lo2) * el_max + (1.f / 262144.f) * mag +
-                          (1.f / 1048576.f) * mag;
-        tau[tok] = 2.f * eps;  // NaN / inf coordinates give a NaN / inf tau: the token is re-searched exactly
-    }
+    (void)header;
+    // |z|, |z - zh - zl|, |zl| (NaN / inf coordinates propagate: the token is then re-searched exactly)
+    if (ok) tok_norms[tok] = make_float4(sqrtf(zz), sqrtf(res), sqrtf(lo2), 0.f);
 }
 
 // ---------------------------------------------------------------------------
@@ -131,7 +122,8 @@ struct LowParams {
     const float* a_img;        // token image, n_m_tiles tiles
     const float* b_img;        // codebook image, Kpad / 128 tiles
     const int* header;
-    const float* tau;
+    const float4* tok_norms;   // per token: |z|, |z - zh - zl|, |zl|
+    const float* cmax;         // [Kpad/32] max code norm per 32-code chunk
     int32_t* chunk;            // [N] winning 32-code chunk
     int32_t* list;             // tokens that need the exact full search
     int32_t* list_count;
@@ -257,6 +249,8 @@ __global__ void __launch_bounds__(kLowThreads, 2) search_tclow_kernel(LowParams 
         const int par = (warp - 4) >> 2;   // code tiles with (nt & 1) == par
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const int first_nan = p.header[0];
+        const float e_max = sqrtf(2.f * __int_as_float(p.header[4]));
+        const float rho_r = __int_as_float(p.header[12]), rho_l = __int_as_float(p.header[14]);
         const int row_in_tile = q * 32 + lane;
         for (int round = 0; round < n_rounds; ++round) {
             const int mt = blockIdx.x + round * gridDim.x;
@@ -317,8 +311,26 @@ __global__ void __launch_bounds__(kLowThreads, 2) search_tclow_kernel(LowParams 
                 const float b2 = fminf(fminf(m2, o2), fmaxf(m1, o1));
                 const int bid = (o1 < m1) ? oid : id;
                 p.chunk[row] = bid;
+                // Error of the approximate score of a code of norm n (Cauchy-Schwarz on the measured split
+                // residuals: |r_e| <= rho_r n, |el| <= rho_l n for every code; fp32 accumulation of <= 8*steps
+                // exact products inside the tensor core 2^-18 of the term magnitudes, 2^-20 for the
+                // three-piece half norm and this estimate itself):
+                //   eps(n) = (|r_z| + |z| rho_r + |zl| rho_l) n + (2^-18 + 2^-20) (|z| n + n^2/2)
+                // Winner-norm argument as in vqb_search_tc16.cu: the approximate winner sits in chunk bid
+                // (norm <= n1), exact_best <= U = b1 + eps(n1); codes with norm > n0 = |z| + sqrt(|z|^2 + 2U)
+                // cannot win; all others have error <= eps(n0)  =>  tau = eps(n0) + eps(n1).
+                const float4 tn = p.tok_norms[row];
+                const float zn = tn.x;
+                const float alpha = tn.y + zn * rho_r + tn.z * rho_l;
+                const float kacc = 1.f / 262144.f + 1.f / 1048576.f;
+                const float n1 = fminf(__ldg(p.cmax + bid), e_max);
+                const float eps1 = alpha * n1 + kacc * (zn * n1 + 0.5f * n1 * n1);
+                const float U = b1 + eps1;
+                const float n0 = fminf(zn + sqrtf(fmaxf(zn * zn + 2.f * U, 0.f)), e_max);
+                const float eps0 = alpha * n0 + kacc * (zn * n0 + 0.5f * n0 * n0);
+                const float tau = 1.0001f * (eps0 + eps1);
                 // sure iff no code outside the winning chunk can beat it (false for NaN / inf anywhere)
-                const bool sure = (b2 - b1 > p.tau[row]) && (b1 < 1e37f) && (first_nan >= p.K);
+                const bool sure = (b2 - b1 > tau) && (b1 < 1e37f) && (first_nan >= p.K);
                 if (!sure) {
                     const int slot = atomicAdd(p.list_count, 1);
                     p.list[slot] = (int32_t)row;
@@ -425,7 +437,7 @@ static LowWorkspace low_workspace(int64_t N, int D) {
     w.off_img = off;
     off = round_up_z(off + sizeof(float) * tclow_tile_floats(D) * n_m_tiles, 1024);
     w.off_tau = off;
-    off = round_up_z(off + 4 * (size_t)N, 1024);
+    off = round_up_z(off + 16 * (size_t)N, 1024);
     w.off_chunk = off;
     off = round_up_z(off + 4 * (size_t)N, 1024);
     w.off_list = off;
@@ -496,13 +508,13 @@ static int launch_tclow_d(const float* z, int64_t N, int64_t HW, const float* E,
                           const PackLayout& L, unsigned char* wsb, const LowWorkspace& w, int64_t* idx_out,
                           float* dmin_out, cudaStream_t s) {
     float* img = reinterpret_cast<float*>(wsb + w.off_img);
-    float* tau = reinterpret_cast<float*>(wsb + w.off_tau);
+    float4* tok_norms = reinterpret_cast<float4*>(wsb + w.off_tau);
     int32_t* chunk = reinterpret_cast<int32_t*>(wsb + w.off_chunk);
     int32_t* list = reinterpret_cast<int32_t*>(wsb + w.off_list);
     int32_t* count = reinterpret_cast<int32_t*>(wsb + w.off_count);
     const unsigned n_m_tiles = (unsigned)((N + kLowRows - 1) / kLowRows);
     VQB_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int32_t), s));
-    split_tf32_tokens_kernel<D><<<n_m_tiles, 128, 0, s>>>(z, N, HW, reinterpret_cast<const int*>(pk), img, tau);
+    split_tf32_tokens_kernel<D><<<n_m_tiles, 128, 0, s>>>(z, N, HW, reinterpret_cast<const int*>(pk), img, tok_norms);
     VQB_LAUNCH_CHECK("split_tf32_tokens_kernel");
     LowParams p;
     p.N = N;
@@ -513,7 +525,8 @@ static int launch_tclow_d(const float* z, int64_t N, int64_t HW, const float* E,
     p.a_img = img;
     p.b_img = reinterpret_cast<const float*>(pk + L.off_img);
     p.header = reinterpret_cast<const int*>(pk);
-    p.tau = tau;
+    p.tok_norms = tok_norms;
+    p.cmax = reinterpret_cast<const float*>(pk + L.off_cmax);
     p.chunk = chunk;
     p.list = list;
     p.list_count = count;
