@@ -536,6 +536,9 @@ def run_gpu_arm(args):
         z = zt.requires_grad_(True)
         weight.grad = None
         z_q, loss_dict, idx = vq_sync(z)  # reference contract: Python floats in loss_dict (host sync)
+        # the step's loss is read on the host here (forward() has just synchronised for the two logged
+        # floats, so this costs no second wait); the backward then runs while the host prepares step i+1
+        loss_value = loss_dict["vq_loss"].item()
         torch.autograd.backward((z_q, loss_dict["vq_loss"]), (gs[i % len(gs)], one))
         if world > 1:
             usage, _, _ = ops.codebook_usage(idx, K)
@@ -549,7 +552,7 @@ def run_gpu_arm(args):
             d2h_stream.wait_event(ready)
             idx_host.copy_(idx, non_blocking=True)
             idx.record_stream(d2h_stream)
-        return loss_dict["vq_loss"].item(), nxt
+        return loss_value, nxt
 
     e2e_steps = max(3, min(args.steps, 20))
     staged = prefetch(0)
