@@ -4,6 +4,7 @@ PyTorch is the tensor / stream / autograd carrier only: every op validates its
 arguments, allocates outputs with torch, and enqueues libvqb200 kernels on the
 current CUDA stream.  CPU tensors are rejected -- there is no fallback path.
 """
+import contextlib
 import ctypes
 from typing import Optional, Tuple
 
@@ -72,6 +73,13 @@ def _shape_bdhw(z: Tensor, weight: Tensor) -> Tuple[int, int, int, int]:
     return B, D, HW, int(weight.shape[0])
 
 
+def _on(device):
+    """Device guard that costs nothing when `device` is already current (the common case)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return contextlib.nullcontext()
+    return torch.cuda.device(device)
+
+
 def _bytes(n: int, device) -> Tensor:
     return torch.empty(max(int(n), 1), dtype=torch.uint8, device=device)
 
@@ -92,7 +100,7 @@ def _search_into(z: Tensor, weight: Tensor, algo: int, want_dmin: bool):
     pack = _prepare(weight)
     idx = torch.empty((B,) + tuple(z.shape[2:]), dtype=torch.int64, device=dev)
     dmin = torch.empty(idx.shape, dtype=torch.float32, device=dev) if want_dmin else None
-    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    stats = torch.empty(4, dtype=torch.int64, device=dev)  # every search path writes all four entries
     ws_bytes = lib().vqb_search_workspace_bytes(B, D, HW, K, algo)
     ws = _bytes(ws_bytes, dev)
     prof = PROFILE
@@ -124,7 +132,7 @@ def search(z: Tensor, weight: Tensor, algo: int = 0) -> Tuple[Tensor, Tensor, Te
         return (torch.empty(shape, dtype=torch.int64, device=z.device),
                 torch.empty(shape, dtype=torch.float32, device=z.device),
                 torch.zeros(4, dtype=torch.int64, device=z.device))
-    with torch.cuda.device(z.device):
+    with _on(z.device):
         idx, dmin, stats = _search_into(z, weight, algo, True)
     return idx, dmin, stats
 
@@ -155,7 +163,7 @@ def quantize(z: Tensor, weight: Tensor, beta: float, algo: int = 0
         return (torch.empty_like(z), nan, nan.clone(),
                 torch.empty((B,) + tuple(z.shape[2:]), dtype=torch.int64, device=z.device),
                 torch.zeros(4, dtype=torch.int64, device=z.device))
-    with torch.cuda.device(z.device):
+    with _on(z.device):
         idx, _, stats = _search_into(z, weight, algo, False)
         z_q = torch.empty_like(z)
         loss = torch.empty(2, dtype=torch.float32, device=z.device)
@@ -196,7 +204,7 @@ def quantize_backward(z: Tensor, weight: Tensor, indices: Tensor, g_zq: Optional
         g_vq = g_vq.reshape(1).to(torch.float32).contiguous()
     if z.numel() == 0:
         return torch.empty_like(z), (torch.zeros_like(weight) if need_dE else weight.new_empty((0,)))
-    with torch.cuda.device(z.device):
+    with _on(z.device):
         dz = torch.empty_like(z)
         dE = torch.zeros_like(weight) if need_dE else None
         prof = PROFILE_BWD
@@ -254,7 +262,7 @@ def codebook_entry(weight: Tensor, indices: Tensor) -> Tuple[Tensor, Tensor]:
     err = torch.zeros(1, dtype=torch.int32, device=weight.device)
     if indices.numel() == 0:
         return out, err
-    with torch.cuda.device(weight.device):
+    with _on(weight.device):
         check(lib().vqb_gather_f32(_p(weight), _p(indices), B, D, HW, K, _p(out), _p(err), _stream()),
               "vqb_gather_f32")
         _count("gather")
@@ -276,7 +284,7 @@ def codebook_usage(indices: Tensor, num_embeddings: int) -> Tuple[Tensor, Tensor
     hist = torch.empty(num_embeddings, dtype=torch.int64, device=indices.device)
     used = torch.empty(1, dtype=torch.int64, device=indices.device)
     err = torch.zeros(1, dtype=torch.int32, device=indices.device)
-    with torch.cuda.device(indices.device):
+    with _on(indices.device):
         check(lib().vqb_hist_i64(_p(indices), indices.numel(), num_embeddings, _p(hist), _p(used),
                                  _p(err), _stream()), "vqb_hist_i64")
         _count("hist")
@@ -302,7 +310,7 @@ def code_sums(z: Tensor, indices: Tensor, num_embeddings: int) -> Tuple[Tensor, 
     HW = z.numel() // max(B * D, 1)
     counts = torch.zeros(num_embeddings, dtype=torch.float32, device=z.device)
     sums = torch.zeros(num_embeddings, D, dtype=torch.float32, device=z.device)
-    with torch.cuda.device(z.device):
+    with _on(z.device):
         check(lib().vqb_code_sums_f32(_p(z), _p(indices), B, D, HW, num_embeddings, _p(counts),
                                       _p(sums), _stream()), "vqb_code_sums_f32")
     return counts, sums
@@ -324,7 +332,7 @@ def ema_update(weight: Tensor, cluster_size: Tensor, embed_sum: Tensor, counts: 
             raise RuntimeError(f"{n} must be contiguous")
     K, D = int(weight.shape[0]), int(weight.shape[1])
     scratch = torch.empty(1, dtype=torch.float32, device=weight.device)
-    with torch.cuda.device(weight.device):
+    with _on(weight.device):
         check(lib().vqb_ema_update_f32(_p(weight), _p(cluster_size), _p(embed_sum), _p(counts),
                                        _p(sums), K, D, float(decay), float(eps), _p(scratch),
                                        _stream()), "vqb_ema_update_f32")
@@ -336,7 +344,7 @@ def pack_argmin_keys(dmin: Tensor, indices: Tensor, index_offset: int) -> Tensor
     dmin = dmin.contiguous()
     indices = indices.contiguous()
     keys = torch.empty(indices.shape, dtype=torch.int64, device=dmin.device)
-    with torch.cuda.device(dmin.device):
+    with _on(dmin.device):
         check(lib().vqb_pack_argmin_keys(_p(dmin), _p(indices), indices.numel(), int(index_offset),
                                          _p(keys), _stream()), "vqb_pack_argmin_keys")
     return keys
@@ -354,7 +362,7 @@ def unpack_argmin_keys(keys: Tensor) -> Tuple[Tensor, Tensor]:
     keys = keys.contiguous()
     idx = torch.empty_like(keys)
     dmin = torch.empty(keys.shape, dtype=torch.float32, device=keys.device)
-    with torch.cuda.device(keys.device):
+    with _on(keys.device):
         check(lib().vqb_unpack_argmin_keys(_p(keys), keys.numel(), _p(idx), _p(dmin), _stream()),
               "vqb_unpack_argmin_keys")
     return idx, dmin
@@ -376,7 +384,7 @@ def stats_pack(dE: Tensor, hist: Optional[Tensor], scalars: Optional[Tensor]) ->
     if hist is not None:
         hist = hist.reshape(-1).long().contiguous()
     flat = torch.empty(dE.numel() + n_s + 2 * n_h, dtype=torch.float32, device=dE.device)
-    with torch.cuda.device(dE.device):
+    with _on(dE.device):
         check(lib().vqb_stats_pack(_p(dE), dE.numel(), _p(scalars), n_s, _p(hist), n_h, _p(flat), _stream()),
               "vqb_stats_pack")
         _count("keys")
@@ -391,7 +399,7 @@ def stats_unpack(flat: Tensor, dE_shape, n_scalars: int, n_hist: int, dE_scale: 
     dE = torch.empty(tuple(dE_shape), dtype=torch.float32, device=flat.device)
     scalars = torch.empty(n_scalars, dtype=torch.float32, device=flat.device) if n_scalars else None
     hist = torch.empty(n_hist, dtype=torch.int64, device=flat.device) if n_hist else None
-    with torch.cuda.device(flat.device):
+    with _on(flat.device):
         check(lib().vqb_stats_unpack(_p(flat), n_dE, n_scalars, n_hist, float(dE_scale), _p(dE), _p(scalars), _p(hist),
                                      _stream()), "vqb_stats_unpack")
         _count("keys")
@@ -412,7 +420,7 @@ def indices_narrow(indices: Tensor, num_embeddings: int) -> Tuple[Tensor, Tensor
         raise RuntimeError("num_embeddings must be positive")
     codes = torch.empty(indices.shape, dtype=_NARROW_DTYPES[w], device=indices.device)
     err = torch.zeros(1, dtype=torch.int32, device=indices.device)
-    with torch.cuda.device(indices.device):
+    with _on(indices.device):
         check(lib().vqb_indices_narrow(_p(indices), indices.numel(), int(num_embeddings), _p(codes), w,
                                        _p(err), _stream()), "vqb_indices_narrow")
         _count("keys")
@@ -433,7 +441,7 @@ def indices_widen(codes: Tensor) -> Tensor:
         raise RuntimeError("codes must be a CUDA uint8 / uint16 / int32 tensor")
     codes = codes.contiguous()
     out = torch.empty(codes.shape, dtype=torch.int64, device=codes.device)
-    with torch.cuda.device(codes.device):
+    with _on(codes.device):
         check(lib().vqb_indices_widen(_p(codes), codes.numel(), codes.element_size(), _p(out), _stream()),
               "vqb_indices_widen")
         _count("keys")
@@ -468,7 +476,7 @@ def conv1x1(x: Tensor, weight: Tensor, bias: Optional[Tensor], algo: int = 0) ->
     y = torch.empty((B, Cout) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
     if y.numel() == 0:
         return y
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         wb = lib().vqb_conv1x1_workspace_bytes(Cin, Cout)
         ws = _bytes(wb, x.device)
         prof = PROFILE_CONV
