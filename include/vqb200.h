@@ -181,6 +181,10 @@ VQB_API int vqb_conv1x1_f32(const float* x, int64_t B, int Cin, int64_t HW, cons
  * returns the flop count issued; the caller times it with CUDA events. */
 VQB_API int vqb_fma_peak_launch(int packed, int iters, float* sink, double* flops_host,
                         vqb_stream_t stream);
+/* access-pattern ceiling of the tiled tail kernels: mode 0 strided copy out = a,
+ * mode 1 out = a + b, mode 2 linear float4 copy; tensors [B, D, HW] fp32, D % 64 == 0 */
+VQB_API int vqb_ubench_copy(const float* a, const float* b, float* out, int64_t B, int D, int64_t HW, int mode,
+                    vqb_stream_t stream);
 
 /* instruction-mix microbenchmarks of the low-D inner loop (modes in csrc/vqb_ubench.cu);
  * src: >= 10240 floats of finite data */

@@ -117,9 +117,85 @@ __global__ void __launch_bounds__(256, 2) ubench_kernel(int sweeps, const float*
     if (r == 123.456f) sink[0] = r;
 }
 
+// Access-pattern ceiling of the tiled tail kernels: the same CTA mapping (32 consecutive tokens x 8 warps, each
+// thread walks channels ty, ty+8, ... of its token, 128-byte requests 4*HW bytes apart) as a pure copy, i.e.
+// without the codebook gather, the transposing tile and the barriers.  mode 0: out = in; mode 1: out = a + b
+// (two input streams like the backward); mode 2: linear float4 copy of the same bytes for comparison.
+__global__ void __launch_bounds__(256)
+    pattern_copy_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t N,
+                        int D, int64_t HW, int mode) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (mode == 2) {
+        const int64_t n4 = N * D / 4;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+            reinterpret_cast<float4*>(out)[i] = __ldg(reinterpret_cast<const float4*>(a) + i);
+        return;
+    }
+    if (mode >= 3) {  // 3: out = a, 4: out = a + b with 128 tokens per CTA, one float4 (4 tokens) per lane
+        const int64_t tok4 = (int64_t)blockIdx.x * 128 + 4 * tx;
+        if (tok4 >= N) return;
+        const int64_t b4 = tok4 / HW;
+        const int64_t off4 = (b4 * D) * HW + (tok4 - b4 * HW) + (int64_t)ty * HW;
+        const int64_t step4 = 8 * HW;
+        for (int d0 = 0; d0 < D; d0 += 64) {
+            float4 v[8], w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldg(reinterpret_cast<const float4*>(a + off4 + (int64_t)d0 * HW + i * step4));
+            if (mode == 4) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    w[i] = __ldg(reinterpret_cast<const float4*>(b + off4 + (int64_t)d0 * HW + i * step4));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 r = v[i];
+                if (mode == 4) {
+                    r.x += w[i].x;
+                    r.y += w[i].y;
+                    r.z += w[i].z;
+                    r.w += w[i].w;
+                }
+                *reinterpret_cast<float4*>(out + off4 + (int64_t)d0 * HW + i * step4) = r;
+            }
+        }
+        return;
+    }
+    const int64_t tok = (int64_t)blockIdx.x * 32 + tx;
+    if (tok >= N) return;
+    const int64_t bi = tok / HW;
+    const int64_t off = (bi * D) * HW + (tok - bi * HW) + (int64_t)ty * HW;
+    const int64_t step = 8 * HW;
+    for (int d0 = 0; d0 < D; d0 += 64) {
+        float v[8], w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __ldg(a + off + (int64_t)d0 * HW + i * step);
+        if (mode == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = __ldg(b + off + (int64_t)d0 * HW + i * step);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[off + (int64_t)d0 * HW + i * step] = mode == 1 ? v[i] + w[i] : v[i];
+    }
+}
+
 }  // namespace vqb
 
 using namespace vqb;
+
+extern "C" int vqb_ubench_copy(const float* a, const float* b, float* out, int64_t B, int D, int64_t HW, int mode,
+                               vqb_stream_t stream) {
+    if (!a || !out || ((mode == 1 || mode == 4) && !b) || B <= 0 || D <= 0 || D % 64 != 0 || HW <= 0 || HW % 4 != 0 || mode < 0 ||
+        mode > 4) {
+        set_error("vqb_ubench_copy: invalid argument");
+        return VQB_ERR_INVALID_ARG;
+    }
+    const int64_t N = B * HW;
+    const unsigned blocks = mode == 2 ? (unsigned)(sm_count() * 16)
+                                      : (mode >= 3 ? (unsigned)((N + 127) / 128) : (unsigned)((N + 31) / 32));
+    pattern_copy_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, N, D, HW, mode);
+    VQB_LAUNCH_CHECK("pattern_copy_kernel");
+    return VQB_OK;
+}
 
 extern "C" int vqb_ubench_launch(int mode, int sweeps, const float* src, float* sink, double* flops_host,
                                  vqb_stream_t stream) {
