@@ -365,6 +365,125 @@ __global__ void __launch_bounds__(256, DC <= 64 ? 4 : (DC <= 128 ? 3 : 2))
     }
 }
 
+// ---------------------------------------------------------------------------
+// 128 tokens per CTA, one float4 (4 consecutive tokens) per lane: a warp instruction moves 512 contiguous bytes
+// of one channel row.  Measured ceiling of this access pattern (scripts/pattern_copy.py): 6.6-6.7 TB/s, the
+// same as a linear copy, against 4.2-5.7 TB/s for 128-byte segments.  Needs HW % 4 == 0 and 16-byte aligned
+// tensors (a quad of tokens never straddles two images then); anything else takes the 32-token kernels above.
+// ---------------------------------------------------------------------------
+constexpr int kTok128 = 128;
+constexpr int kTok128Stride = kTok128 + 4;  // floats; keeps rows 16-byte aligned
+
+struct Tile128Tokens {
+    int64_t off[kTok128 / 4];  // element offset of (first token of the quad, channel 0); -1 past N
+    int code[kTok128];
+};
+
+__device__ __forceinline__ void tile128_load_tokens(Tile128Tokens& tt, const int64_t* __restrict__ idx, int64_t N,
+                                                    int D, int64_t HW, int K, int* err_flag) {
+    if (threadIdx.x < kTok128) {
+        const int64_t tok = (int64_t)blockIdx.x * kTok128 + threadIdx.x;
+        int k = 0;
+        if (tok < N) {
+            int64_t kk = idx[tok];
+            if (kk < 0 || kk >= K) {
+                if (err_flag) *err_flag = 1;
+                kk = 0;
+            }
+            k = (int)kk;
+        }
+        tt.code[threadIdx.x] = k;
+        if ((threadIdx.x & 3) == 0) {
+            int64_t off = -1;
+            if (tok < N) {
+                const int64_t b = tok / HW;
+                off = (b * D) * HW + (tok - b * HW);
+            }
+            tt.off[threadIdx.x >> 2] = off;
+        }
+    }
+}
+
+// codebook rows of the CTA's 128 tokens, channels [d0, d0+DC) -> tile[channel][token]; warp w stages tokens
+// 16w .. 16w+15, lane = channel (full 128-byte lines from L2)
+template <int DC>
+__device__ __forceinline__ void tile128_fill_codes(float (*tile)[kTok128Stride], const Tile128Tokens& tt,
+                                                   const float* __restrict__ E, int D, int d0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const int t = warp * 16 + i;
+        const float* erow = E + (size_t)tt.code[t] * D + d0 + lane;
+#pragma unroll
+        for (int c = 0; c < DC / 32; ++c) tile[lane + 32 * c][t] = __ldg(erow + 32 * c);
+    }
+}
+
+template <int DC>
+__global__ void __launch_bounds__(256, 3)
+    gather_loss_st_tok128_kernel(const float* __restrict__ z, const float* __restrict__ E,
+                                 const int64_t* __restrict__ idx, int64_t N, int D, int64_t HW, int K,
+                                 float* __restrict__ zq_out, double* __restrict__ partials,
+                                 int* __restrict__ err_flag) {
+    constexpr int R = DC / 8;  // channels per thread per pass
+    __shared__ __align__(16) float tile[DC][kTok128Stride];
+    __shared__ Tile128Tokens tt;
+    __shared__ double warp_part[8];
+    const int tq = threadIdx.x & 31, cy = threadIdx.x >> 5;
+    tile128_load_tokens(tt, idx, N, D, HW, K, err_flag);
+    __syncthreads();
+    const int64_t off = tt.off[tq];
+    const int64_t step = 8 * HW;
+    float sq = 0.f;
+    for (int d0 = 0; d0 < D; d0 += DC) {
+        float4 zv[R];
+        if (off >= 0) {
+            const float* zp = z + off + (int64_t)(d0 + cy) * HW;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                zv[i] = __ldg(reinterpret_cast<const float4*>(zp));
+                zp += step;
+            }
+        }
+        if (d0 > 0) __syncthreads();  // the previous pass is done with the tile
+        tile128_fill_codes<DC>(tile, tt, E, D, d0);
+        __syncthreads();
+        if (off >= 0) {
+            float* qp = zq_out + off + (int64_t)(d0 + cy) * HW;
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                const float4 e = *reinterpret_cast<const float4*>(&tile[cy + 8 * i][4 * tq]);
+                float4 q;
+                const float dx = __fsub_rn(e.x, zv[i].x), dy = __fsub_rn(e.y, zv[i].y);
+                const float dz = __fsub_rn(e.z, zv[i].z), dw = __fsub_rn(e.w, zv[i].w);
+                q.x = __fadd_rn(zv[i].x, dx);
+                q.y = __fadd_rn(zv[i].y, dy);
+                q.z = __fadd_rn(zv[i].z, dz);
+                q.w = __fadd_rn(zv[i].w, dw);
+                *reinterpret_cast<float4*>(qp) = q;
+                qp += step;
+                sq = fmaf(dx, dx, sq);
+                sq = fmaf(dy, dy, sq);
+                sq = fmaf(dz, dz, sq);
+                sq = fmaf(dw, dw, sq);
+            }
+        }
+    }
+    double v = warp_sum_f64((double)sq);
+    if (tq == 0) warp_part[cy] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += warp_part[w];
+        partials[blockIdx.x] = s;
+    }
+}
+
+static bool tok128_ok(int D, int64_t HW, const void* a, const void* b) {
+    return D % 32 == 0 && HW % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) == 0;
+}
+
 // largest pass width (channels) that divides D; the backward keeps z and g in registers -> half of it
 static int tiled_pass_width(int D, int cap) {
     for (int dc = cap; dc >= 64; dc -= 64)
@@ -590,9 +709,12 @@ static int check_shape(int64_t B, int D, int64_t HW, int K) {
 
 static int g_bwd_pass_cap = 64;   // measured best on B200 (profiles/r01_tail_pass_width_sweep.txt)
 static int g_fwd_pass_cap = 64;
+static int g_tail_tok128 = 1;  // 128-token float4 kernels when the layout allows (vqb_tune "tail_tok128", 0 = off)
 namespace vqb {
 void set_bwd_pass_cap(int c) {
-    if (c >= 1024) g_fwd_pass_cap = c - 1024; else g_bwd_pass_cap = c;
+    if (c >= 2048) g_tail_tok128 = c - 2048;
+    else if (c >= 1024) g_fwd_pass_cap = c - 1024;
+    else g_bwd_pass_cap = c;
 }
 }  // namespace vqb
 
@@ -624,6 +746,19 @@ extern "C" int vqb_gather_loss_st_f32(const float* z, const float* E, const int6
     }
     const dim3 block(sh.tx, sh.slices);
     double* parts = static_cast<double*>(partials);
+    // measured (scripts/tail_ab.py): 0.083 -> 0.046 ms at D=32, 0.146 -> 0.138 at D=64 (512 K / 1 M tokens), but
+    // 0.46 -> 0.59 ms at D=256 where the four fill/barrier rounds per CTA dominate: small D only
+    if (g_tail_tok128 && D <= 64 && tok128_ok(D, HW, z, zq_out)) {
+        const int64_t tb = (N + kTok128 - 1) / kTok128;
+        if (D % 64 == 0)
+            gather_loss_st_tok128_kernel<64><<<(unsigned)tb, 256, 0, s>>>(z, E, idx, N, D, HW, K, zq_out, parts, err_flag);
+        else
+            gather_loss_st_tok128_kernel<32><<<(unsigned)tb, 256, 0, s>>>(z, E, idx, N, D, HW, K, zq_out, parts, err_flag);
+        VQB_LAUNCH_CHECK("gather_loss_st_tok128_kernel");
+        loss_finalize_kernel<<<1, 256, 0, s>>>(parts, tb, 1.0 / ((double)N * D), beta, loss_out);
+        VQB_LAUNCH_CHECK("loss_finalize_kernel");
+        return VQB_OK;
+    }
     if (D % 32 == 0) {
         const int64_t tb = (N + kTileTok - 1) / kTileTok;
 #define VQB_GATHER(dc) \
