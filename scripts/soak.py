@@ -1,0 +1,107 @@
+"""Soak run: many random shapes through every search kernel, the forward/backward tail and the 1x1 convolution,
+each checked against float64 (search: chosen score within float32 rounding of the best; the low-D tensor path
+must equal the FMA kernel exactly).  Prints one line per failure and a summary; exit code 1 on any failure."""
+import os, sys, time
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vq_gan_b200 import VectorQuantizer, ops
+
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+fails = 0
+t_start = time.time()
+for case in range(n_cases):
+    D = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 11, 16, 17, 31, 32, 40, 64, 65, 96, 128, 130, 192, 200, 256, 257, 300]))
+    K = int(rng.choice([1, 2, 3, 31, 32, 33, 127, 128, 129, 255, 256, 257, 511, 1000, 2048, 4100, 9000]))
+    B = int(rng.integers(1, 7))
+    HW = int(rng.choice([1, 3, 4, 31, 32, 33, 100, 128, 256, 1000, 1024, 4096, 20000]))
+    if B * HW * K * D > 3e10:
+        HW = max(1, int(3e10 / (B * K * D)))
+    seed = int(rng.integers(0, 1 << 30))
+    g = torch.Generator().manual_seed(seed)
+    scale = float(rng.choice([1.0, 1.0, 1e-3, 1e3]))
+    z = torch.randn(B, D, HW, generator=g) * scale
+    E = torch.randn(K, D, generator=g) * float(rng.choice([1.0, 1.0, 1e-2, 1e2]))
+    zc, Ec = z.cuda(), E.cuda()
+    rows = z.permute(0, 2, 1).reshape(-1, D).double()
+    d64 = 0.5 * (E.double() ** 2).sum(1)[None, :] - rows @ E.double().t()
+    best = d64.min(1).values
+    sc = (rows.norm(dim=1) * E.double().norm(dim=1).max() + 0.5 * (E.double() ** 2).sum(1).max()).clamp_min(1e-300)
+    algos = [0, 2]
+    if D <= 16:
+        algos += [1, 5]
+    if 16 < D <= 256:
+        algos.append(4)
+    if D % 64 == 0 and D <= 256:
+        algos.append(3)
+    res = {}
+    for a in algos:
+        try:
+            idx, dmin, st = ops.search(zc, Ec, a)
+            torch.cuda.synchronize()
+        except Exception as ex:  # noqa: BLE001
+            print(f"FAIL case {case} D={D} K={K} B={B} HW={HW} algo={a}: {type(ex).__name__}: {ex}", flush=True)
+            fails += 1
+            continue
+        res[a] = (idx, dmin)
+        chosen = d64.gather(1, idx.reshape(-1, 1).cpu()).squeeze(1)
+        worst = float(((chosen - best) / sc).max())
+        if not (worst < 2e-6) or int(idx.min()) < 0 or int(idx.max()) >= K:
+            print(f"FAIL case {case} D={D} K={K} B={B} HW={HW} seed={seed} algo={a}: worst rel excess {worst:.3e}", flush=True)
+            fails += 1
+    if 1 in res and 5 in res and not (torch.equal(res[1][0], res[5][0]) and torch.equal(res[1][1], res[5][1])):
+        print(f"FAIL case {case} D={D} K={K} B={B} HW={HW} seed={seed}: algo 5 != algo 1", flush=True)
+        fails += 1
+    # module forward + backward against float64 on the returned indices
+    vq = VectorQuantizer(K, D, 0.25, lazy_stats=True).cuda()
+    with torch.no_grad():
+        vq.embedding.weight.copy_(Ec)
+    zin = zc.view(B, D, HW, 1).clone().requires_grad_(True)
+    gz = torch.randn(B, D, HW, 1, generator=g).cuda()
+    zq, ld, idx = vq(zin)
+    torch.autograd.backward((zq, ld["vq_loss"]), (gz, torch.ones((), device="cuda")))
+    torch.cuda.synchronize()
+    e = E[idx.reshape(-1).cpu()].double()
+    mse = float(((e - rows) ** 2).mean())
+    if abs(float(ld["codebook_loss"]) - mse) > 1e-5 * max(mse, 1e-30):
+        print(f"FAIL case {case} D={D} K={K} B={B} HW={HW}: mse {float(ld['codebook_loss'])} vs {mse}", flush=True)
+        fails += 1
+    n = z.numel()
+    dz_ref = gz.cpu().double().view(B, D, HW).permute(0, 2, 1).reshape(-1, D) + 2.0 / n * (rows - e)
+    dz = zin.grad.cpu().double().view(B, D, HW).permute(0, 2, 1).reshape(-1, D)
+    if float((dz - dz_ref).abs().max()) > 1e-5 * float(dz_ref.abs().max() + 1e-30):
+        print(f"FAIL case {case} D={D} K={K} B={B} HW={HW}: dz", flush=True)
+        fails += 1
+    terms = 0.25 * 2.0 / n * (e - rows)
+    dE_ref = torch.zeros(K, D, dtype=torch.float64).index_add_(0, idx.reshape(-1).cpu(), terms)
+    # fp32 atomic accumulation: the error scales with the sum of |terms| of a code (cancellation), not with the result
+    dE_mag = torch.zeros(K, D, dtype=torch.float64).index_add_(0, idx.reshape(-1).cpu(), terms.abs())
+    dE = vq.embedding.weight.grad.cpu().double()
+    cnt = torch.bincount(idx.reshape(-1).cpu(), minlength=K).double().clamp_min(1.0).sqrt().unsqueeze(1)
+    # fp32 atomic accumulation of c terms: error ~ 2^-24 * sqrt(c) * sum|terms| (random walk on the running sum)
+    if float(((dE - dE_ref).abs() / (cnt * dE_mag + 1e-300)).max()) > 1e-6:
+        # long one-sided sums lose bits in ANY fp32 accumulation: accept what stock torch (fp32 index_add on the
+        # GPU) achieves on the same terms, within a factor of 4
+        tt = torch.zeros(K, D, device="cuda").index_add_(
+            0, idx.reshape(-1), (0.25 * 2.0 / n * (Ec[idx.reshape(-1)] - zc.permute(0, 2, 1).reshape(-1, D))))
+        terr = float((tt.cpu().double() - dE_ref).abs().max())
+        err = float((dE - dE_ref).abs().max())
+        if err > 4.0 * terr + 1e-12:
+            print(f"FAIL case {case} D={D} K={K} B={B} HW={HW} zscale={scale} Emax={float(E.abs().max()):.3g}: dE err {err:.3e} "
+                  f"vs torch fp32 index_add err {terr:.3e}, max|dE| {float(dE_ref.abs().max()):.3e}", flush=True)
+            fails += 1
+    # 1x1 convolution
+    if case % 2 == 0:
+        Cout = int(rng.choice([1, 4, 16, 48, 64, 100, 256]))
+        w = torch.randn(Cout, D, generator=g) / max(D, 1) ** 0.5
+        bb = torch.randn(Cout, generator=g)
+        y = ops.conv1x1(zc, w.cuda(), bb.cuda())
+        ref = torch.einsum("oc,bct->bot", w.double(), z.double()) + bb.double().view(1, -1, 1)
+        bound = torch.einsum("oc,bct->bot", w.abs().double(), z.abs().double()) + bb.abs().double().view(1, -1, 1)
+        r = float(((y.cpu().double() - ref).abs() / bound.clamp_min(1e-300)).max())
+        if not r < 3e-6:
+            print(f"FAIL case {case} conv Cin={D} Cout={Cout} B={B} HW={HW}: {r:.3e}", flush=True)
+            fails += 1
+print(f"soak: {n_cases} cases, {fails} failures, {time.time() - t_start:.1f} s")
+sys.exit(1 if fails else 0)
