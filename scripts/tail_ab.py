@@ -3,7 +3,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vq_gan_b200 import VectorQuantizer, ops, _cabi
 lib = _cabi.lib()
-for D, K, B in ((256, 16384, 1024), (64, 4096, 1024), (32, 1024, 512)):
+for D, K, B in ((4, 16384, 1024), (8, 4096, 1024), (64, 4096, 1024), (32, 1024, 512)):
     vq = VectorQuantizer(K, D, lazy_stats=True).cuda()
     with torch.no_grad():
         vq.embedding.weight.copy_(torch.randn(K, D))
