@@ -68,3 +68,37 @@ def test_stats_pack_roundtrip_is_exact_for_large_counts():
     # summing R copies stays exact (what the all-reduce does)
     a, s, h = vdist.unpack_stats(flat * 8.0, dE.shape, 2, hist.numel())
     assert torch.equal(h, hist * 8)
+
+
+def test_quant_conv_is_checkpoint_compatible_with_nn_conv2d():
+    """`pre_quant_conv` / `post_quant_conv` (vq_vae.py:74-79) swap: same parameters and state_dict keys as
+    nn.Conv2d(cin, cout, 1); no CPU path."""
+    from vq_gan_b200 import QuantConv1x1
+    ref = torch.nn.Conv2d(8, 16, kernel_size=1)
+    mine = QuantConv1x1(8, 16)
+    assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+    assert all(mine.state_dict()[k].shape == v.shape for k, v in ref.state_dict().items())
+    mine.load_state_dict(ref.state_dict(), strict=True)
+    with pytest.raises(RuntimeError):
+        mine(torch.randn(1, 8, 4, 4))
+    with pytest.raises(RuntimeError):
+        mine(torch.randn(8, 4, 4))
+
+
+def test_extension_modules_host_contract():
+    from vq_gan_b200 import EMAVectorQuantizer
+    from vq_gan_b200.graphs import GraphedVectorQuantizer
+    torch.manual_seed(42)
+    ema = EMAVectorQuantizer(32, 8, 0.25, decay=0.9)
+    assert sorted(ema.state_dict().keys()) == ["cluster_size", "embed_sum", "embedding.weight"]
+    assert not ema.embedding.weight.requires_grad
+    # same RNG contract as the reference constructor: the codebook equals the plain module's under one seed
+    torch.manual_seed(42)
+    from vq_gan_b200 import VectorQuantizer
+    plain = VectorQuantizer(32, 8, 0.25)
+    assert torch.equal(plain.embedding.weight.detach(), ema.embedding.weight.detach())
+    # a reference checkpoint loads with strict=False (only the two EMA buffers are missing)
+    missing = ema.load_state_dict(plain.state_dict(), strict=False)
+    assert sorted(missing.missing_keys) == ["cluster_size", "embed_sum"] and not missing.unexpected_keys
+    with pytest.raises(RuntimeError):
+        GraphedVectorQuantizer(plain, torch.randn(1, 8, 4, 4))
