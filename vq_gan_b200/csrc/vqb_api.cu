@@ -81,6 +81,10 @@ extern "C" int vqb_tune(const char* key, int value) {
         set_bwd_pass_cap(value);
         return VQB_OK;
     }
+    if (key && strcmp(key, "tail_warp") == 0 && value >= 0 && value <= 2) {
+        set_bwd_pass_cap(4096 + value);
+        return VQB_OK;
+    }
     if (key && strcmp(key, "tail_tok128") == 0 && (value == 0 || value == 1)) {
         set_bwd_pass_cap(2048 + value);
         return VQB_OK;

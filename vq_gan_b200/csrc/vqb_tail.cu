@@ -623,6 +623,71 @@ static bool quad_ok(int D, int64_t HW, const void* a, const void* b, const void*
     return (D == 4 || D == 8) && HW % 4 == 0 && (bits & 15u) == 0;
 }
 
+// ---------------------------------------------------------------------------
+// Warp-private variant of the tiled forward tail (default for D >= 128; vqb_tune "tail_warp").  A warp
+// owns 32 consecutive tokens for ALL channels and transposes its codebook rows through a private 32x33 tile, so
+// the only synchronisation is __syncwarp (the CTA-wide kernel above spends most of its stall time in barriers
+// and on the L2 latency of the gathered rows, profiles/r01_ncu_full_helpers_c3.txt).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+    gather_loss_st_warp_kernel(const float* __restrict__ z, const float* __restrict__ E, const int64_t* __restrict__ idx,
+                               int64_t N, int D, int64_t HW, int K, float* __restrict__ zq_out,
+                               double* __restrict__ partials, int* __restrict__ err_flag) {
+    __shared__ float tiles[8][32][33];
+    __shared__ double warp_part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float (*tile)[33] = tiles[warp];
+    const int64_t tok = ((int64_t)blockIdx.x * 8 + warp) * 32 + lane;
+    const bool live = tok < N;
+    int code = 0;
+    int64_t off = 0;
+    if (live) {
+        int64_t kk = idx[tok];
+        if (kk < 0 || kk >= K) {
+            if (err_flag) *err_flag = 1;
+            kk = 0;
+        }
+        code = (int)kk;
+        const int64_t b = tok / HW;
+        off = (b * D) * HW + (tok - b * HW);
+    }
+    float sq = 0.f;
+    for (int d0 = 0; d0 < D; d0 += 32) {
+        float zv[32];
+        const float* zp = z + off + (int64_t)d0 * HW;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) zv[i] = live ? __ldg(zp + (int64_t)i * HW) : 0.f;
+        float rv[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            const int ct = __shfl_sync(0xffffffffu, code, t);
+            rv[t] = __ldg(E + (size_t)ct * D + d0 + lane);  // row of token t, channel d0 + lane: one 128-byte line
+        }
+#pragma unroll
+        for (int t = 0; t < 32; ++t) tile[lane][t] = rv[t];
+        __syncwarp();
+        if (live) {
+            float* qp = zq_out + off + (int64_t)d0 * HW;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float diff = __fsub_rn(tile[i][lane], zv[i]);
+                qp[(int64_t)i * HW] = __fadd_rn(zv[i], diff);
+                sq = fmaf(diff, diff, sq);
+            }
+        }
+        __syncwarp();
+    }
+    double v = warp_sum_f64((double)sq);
+    if (lane == 0) warp_part[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += warp_part[w];
+        partials[blockIdx.x] = sum;
+    }
+}
+
 // largest pass width (channels) that divides D; the backward keeps z and g in registers -> half of it
 static int tiled_pass_width(int D, int cap) {
     for (int dc = cap; dc >= 64; dc -= 64)
@@ -848,10 +913,12 @@ static int check_shape(int64_t B, int D, int64_t HW, int K) {
 
 static int g_bwd_pass_cap = 64;   // measured best on B200 (profiles/r01_tail_pass_width_sweep.txt)
 static int g_fwd_pass_cap = 64;
+static int g_tail_warp = 1;   // warp-private forward tail (vqb_tune "tail_warp": 0 off, 1 auto = D >= 128, 2 force)
 static int g_tail_tok128 = 1;  // 128-token float4 kernels when the layout allows (vqb_tune "tail_tok128", 0 = off)
 namespace vqb {
 void set_bwd_pass_cap(int c) {
-    if (c >= 2048) g_tail_tok128 = c - 2048;
+    if (c >= 4096) g_tail_warp = c - 4096;
+    else if (c >= 2048) g_tail_tok128 = c - 2048;
     else if (c >= 1024) g_fwd_pass_cap = c - 1024;
     else g_bwd_pass_cap = c;
 }
@@ -895,6 +962,16 @@ extern "C" int vqb_gather_loss_st_f32(const float* z, const float* E, const int6
             gather_loss_st_tok128_kernel<32><<<(unsigned)tb, 256, 0, s>>>(z, E, idx, N, D, HW, K, zq_out, parts, err_flag);
         VQB_LAUNCH_CHECK("gather_loss_st_tok128_kernel");
         loss_finalize_kernel<<<1, 256, 0, s>>>(parts, tb, 1.0 / ((double)N * D), beta, loss_out);
+        VQB_LAUNCH_CHECK("loss_finalize_kernel");
+        return VQB_OK;
+    }
+    // measured (scripts/tail_warp_ab.py): 0.44 ms / 4.9 TB/s at D=256 (CTA-wide kernel 0.46-0.50), 0.227 vs 0.247 ms at
+    // D=128, no gain at D=64: large D only (g_tail_warp: 1 = auto, 0 = off, 2 = force for any D % 32 == 0)
+    if (D % 32 == 0 && ((g_tail_warp == 1 && D >= 128) || g_tail_warp == 2)) {
+        const int64_t wb = (N + 255) / 256;  // 8 warps x 32 tokens per CTA
+        gather_loss_st_warp_kernel<<<(unsigned)wb, 256, 0, s>>>(z, E, idx, N, D, HW, K, zq_out, parts, err_flag);
+        VQB_LAUNCH_CHECK("gather_loss_st_warp_kernel");
+        loss_finalize_kernel<<<1, 256, 0, s>>>(parts, wb, 1.0 / ((double)N * D), beta, loss_out);
         VQB_LAUNCH_CHECK("loss_finalize_kernel");
         return VQB_OK;
     }
