@@ -71,6 +71,7 @@ VQB_API int vqb_device_query(int device, int* sm_count, int* cc_major, int* cc_m
  *                              then wrong by design
  *   "fwd_pass_channels" / "bwd_pass_channels"  64|128|192|256  channels per pass of the tiled tail kernels
  *   "tail_tok128"       0|1   128-token float4 forward-tail kernel for D <= 64 (default 1)
+ *   "bwd_warp"          0|1|2 warp-private backward kernel (experimental, default 0 = off; measured slower)
  *   "tail_warp"         0|1|2 warp-private forward-tail kernel: off / D >= 128 (default) / any D % 32 == 0
  *   "conv_debug"        0..15  bit mask for the 1x1 convolution: 1 no activation loads, 2 no stores,
  *                              4 one MMA in three (timing experiments only) */

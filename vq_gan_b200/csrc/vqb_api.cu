@@ -81,6 +81,10 @@ extern "C" int vqb_tune(const char* key, int value) {
         set_bwd_pass_cap(value);
         return VQB_OK;
     }
+    if (key && strcmp(key, "bwd_warp") == 0 && value >= 0 && value <= 2) {
+        set_bwd_pass_cap(8192 + value);
+        return VQB_OK;
+    }
     if (key && strcmp(key, "tail_warp") == 0 && value >= 0 && value <= 2) {
         set_bwd_pass_cap(4096 + value);
         return VQB_OK;

@@ -688,6 +688,76 @@ __global__ void __launch_bounds__(256, 2)
     }
 }
 
+// Warp-private backward (vqb_tune "bwd_warp": 0 off (default), 1 = D >= 128, 2 = any D % 32 == 0): same idea as
+// gather_loss_st_warp_kernel.  A warp owns 32 consecutive tokens; per 32-channel block it transposes its codebook
+// rows through a private tile, streams z / g / dz with lane = token, leaves the codebook-gradient terms in the
+// tile and scatters them with lane = channel: one 128-byte coalesced red.global.add.f32 per token.
+__global__ void __launch_bounds__(256, 2)
+    backward_warp_kernel(const float* __restrict__ z, const float* __restrict__ E, const int64_t* __restrict__ idx,
+                         const float* __restrict__ g_zq, const float* __restrict__ g_vq, float beta, float norm, int64_t N,
+                         int D, int64_t HW, int K, float* __restrict__ dz_out, float* __restrict__ dE,
+                         unsigned long long* __restrict__ hist) {
+    __shared__ float tiles[8][32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float (*tile)[33] = tiles[warp];
+    const int64_t tok = ((int64_t)blockIdx.x * 8 + warp) * 32 + lane;
+    const bool live = tok < N;
+    const float gv = g_vq ? __ldg(g_vq) : 0.f;
+    const float gbeta = __fmul_rn(gv, beta);
+    int code = 0;
+    int64_t off = 0;
+    if (live) {
+        int64_t kk = idx[tok];
+        if (kk < 0 || kk >= K) kk = 0;
+        code = (int)kk;
+        const int64_t b = tok / HW;
+        off = (b * D) * HW + (tok - b * HW);
+    }
+    const unsigned active = __ballot_sync(0xffffffffu, live);
+    if (hist != nullptr && live) {
+        const unsigned peers = __match_any_sync(active, code);
+        if (lane == __ffs(peers) - 1) atomicAdd(hist + code, (unsigned long long)__popc(peers));
+    }
+    for (int d0 = 0; d0 < D; d0 += 32) {
+        float rv[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            const int ct = __shfl_sync(0xffffffffu, code, t);
+            rv[t] = __ldg(E + (size_t)ct * D + d0 + lane);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float zv[16], gz[16];
+            const int64_t base = off + (int64_t)(d0 + 16 * h) * HW;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) zv[i] = live ? __ldg(z + base + (int64_t)i * HW) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) gz[i] = (live && g_zq) ? __ldg(g_zq + base + (int64_t)i * HW) : 0.f;
+            if (h == 0) {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) tile[lane][t] = rv[t];
+                __syncwarp();
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float e = tile[16 * h + i][lane];
+                const float tt = __fmul_rn(__fmul_rn(norm, __fsub_rn(zv[i], e)), gv);
+                if (live) dz_out[base + (int64_t)i * HW] = __fadd_rn(gz[i], tt);
+                tile[16 * h + i][lane] = __fmul_rn(__fmul_rn(norm, __fsub_rn(e, zv[i])), gbeta);
+            }
+        }
+        __syncwarp();
+        if (dE != nullptr) {
+#pragma unroll 8
+            for (int t = 0; t < 32; ++t) {
+                const int ct = __shfl_sync(0xffffffffu, code, t);
+                if ((active >> t) & 1u) atomicAdd(dE + (size_t)ct * D + d0 + lane, tile[lane][t]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // largest pass width (channels) that divides D; the backward keeps z and g in registers -> half of it
 static int tiled_pass_width(int D, int cap) {
     for (int dc = cap; dc >= 64; dc -= 64)
@@ -913,11 +983,13 @@ static int check_shape(int64_t B, int D, int64_t HW, int K) {
 
 static int g_bwd_pass_cap = 64;   // measured best on B200 (profiles/r01_tail_pass_width_sweep.txt)
 static int g_fwd_pass_cap = 64;
+static int g_bwd_warp = 0;    // warp-private backward (vqb_tune "bwd_warp")
 static int g_tail_warp = 1;   // warp-private forward tail (vqb_tune "tail_warp": 0 off, 1 auto = D >= 128, 2 force)
 static int g_tail_tok128 = 1;  // 128-token float4 kernels when the layout allows (vqb_tune "tail_tok128", 0 = off)
 namespace vqb {
 void set_bwd_pass_cap(int c) {
-    if (c >= 4096) g_tail_warp = c - 4096;
+    if (c >= 8192) g_bwd_warp = c - 8192;
+    else if (c >= 4096) g_tail_warp = c - 4096;
     else if (c >= 2048) g_tail_tok128 = c - 2048;
     else if (c >= 1024) g_fwd_pass_cap = c - 1024;
     else g_bwd_pass_cap = c;
@@ -1033,6 +1105,13 @@ extern "C" int vqb_backward_f32(const float* z, const float* E, const int64_t* i
     const float norm = (float)(2.0 / ((double)N * D));
     unsigned long long* hist = reinterpret_cast<unsigned long long*>(hist_accum);
     const bool v4 = vec4_ok(D, E) && (!dE_accum || (reinterpret_cast<uintptr_t>(dE_accum) & 15u) == 0);
+    if (D % 32 == 0 && ((g_bwd_warp == 1 && D >= 128) || g_bwd_warp == 2)) {
+        const int64_t wb = (N + 255) / 256;
+        backward_warp_kernel<<<(unsigned)wb, 256, 0, s>>>(z, E, idx, g_zq, g_vq, beta, norm, N, D, HW, K, dz_out, dE_accum,
+                                                         hist);
+        VQB_LAUNCH_CHECK("backward_warp_kernel");
+        return VQB_OK;
+    }
     if (D % 32 == 0 && (!dE_accum || (reinterpret_cast<uintptr_t>(dE_accum) & 15u) == 0)) {
         const int64_t tb = (N + kTileTok - 1) / kTileTok;
 #define VQB_BWD(dc)                                                                                            \
