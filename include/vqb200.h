@@ -19,7 +19,11 @@
  *  - every function returns VQB_OK or a negative code, never throws or aborts;
  *    `vqb_last_error()` gives the thread-local message of the last failure;
  *  - the library allocates no user-visible memory: scratch is caller-provided
- *    and sized by the `*_bytes` queries.
+ *    and sized by the `*_bytes` queries;
+ *  - the library holds no mutable process-global state (an immutable per-device
+ *    SM-count cache only) and is re-entrant; every launching entry point fails with
+ *    VQB_ERR_UNSUPPORTED on a device that is not sm_100.  Experiment knobs and
+ *    microbenchmarks live in a separate measurement build (vqb200_bench.h).
  */
 #ifndef VQB200_H
 #define VQB200_H
@@ -61,21 +65,6 @@ VQB_API const char* vqb_last_error(void);
 /* sm count, compute capability and opt-in shared memory of `device` */
 VQB_API int vqb_device_query(int device, int* sm_count, int* cc_major, int* cc_minor,
                      size_t* smem_optin_bytes);
-
-/* Process-wide knobs for experiments; the defaults are the shipped configuration.
- *   "lowd_variant"      0..4   launch shape of the CUDA-core low-D search (0 = 256 threads x 2 CTA/SM);
- *                       16+n   n = 1: one CTA per SM (room for a co-running kernel), n = 0: default
- *   "tc16_cluster"      1|2|4  cluster size (codebook-stage multicast) of the fp16 tensor search
- *   "tclow_cluster"     1|2|4  same for the low-D tensor search; 16+mask skips stages for bisection
- *                              (1 tensor kernel, 2 chunk re-score, 4 exact list search) -- results are
- *                              then wrong by design
- *   "fwd_pass_channels" / "bwd_pass_channels"  64|128|192|256  channels per pass of the tiled tail kernels
- *   "tail_tok128"       0|1   128-token float4 forward-tail kernel for D <= 64 (default 1)
- *   "bwd_warp"          0|1|2 warp-private backward kernel (experimental, default 0 = off; measured slower)
- *   "tail_warp"         0|1|2 warp-private forward-tail kernel: off / D >= 128 (default) / any D % 32 == 0
- *   "conv_debug"        0..15  bit mask for the 1x1 convolution: 1 no activation loads, 2 no stores,
- *                              4 one MMA in three (timing experiments only) */
-VQB_API int vqb_tune(const char* key, int value);
 
 /* ---- codebook pre-pass -------------------------------------------------
  * Replaces `torch.sum(self.embedding.weight ** 2, dim=1)` (quantizer.py:70) and
@@ -177,22 +166,6 @@ VQB_API size_t vqb_conv1x1_workspace_bytes(int Cin, int Cout);
 VQB_API int vqb_conv1x1_f32(const float* x, int64_t B, int Cin, int64_t HW, const float* W,
                     const float* bias, int Cout, float* y, void* workspace, size_t workspace_bytes,
                     int algo, vqb_stream_t stream);
-
-/* ---- measurement --------------------------------------------------------
- * FP32 FMA peak microbenchmark (the low-D roofline denominator): launches a
- * register-resident FFMA (packed=0) or FFMA2 (packed=1) loop on every SM and
- * returns the flop count issued; the caller times it with CUDA events. */
-VQB_API int vqb_fma_peak_launch(int packed, int iters, float* sink, double* flops_host,
-                        vqb_stream_t stream);
-/* access-pattern ceiling of the tiled tail kernels: mode 0 strided copy out = a,
- * mode 1 out = a + b, mode 2 linear float4 copy; tensors [B, D, HW] fp32, D % 64 == 0 */
-VQB_API int vqb_ubench_copy(const float* a, const float* b, float* out, int64_t B, int D, int64_t HW, int mode,
-                    vqb_stream_t stream);
-
-/* instruction-mix microbenchmarks of the low-D inner loop (modes in csrc/vqb_ubench.cu);
- * src: >= 10240 floats of finite data */
-VQB_API int vqb_ubench_launch(int mode, int sweeps, const float* src, float* sink, double* flops_host,
-                      vqb_stream_t stream);
 
 #ifdef __cplusplus
 }

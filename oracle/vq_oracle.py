@@ -225,9 +225,13 @@ def ema_update(codebook: torch.Tensor, cluster_size: torch.Tensor, embed_sum: to
 def argmin_key(dist: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     """Order-preserving int64 key (monotone float bits in the high word, code
     index in the low word) whose signed minimum across codebook shards selects
-    the smallest distance, lowest index on ties."""
-    bits = dist.contiguous().view(torch.int32).to(torch.int64)
+    the smallest distance, lowest index on ties.  A NaN distance (a NaN code:
+    ATen's argmin treats NaN as minimal, quantizer.py:76) packs as the smallest
+    possible key so the lowest NaN index wins across shards."""
+    nan = torch.isnan(dist)
+    bits = (dist + 0.0).contiguous().view(torch.int32).to(torch.int64)  # -0.0 -> +0.0: equal scores must tie
     mono = torch.where(bits < 0, bits ^ 0x7FFFFFFF, bits)
+    mono = torch.where(nan, torch.full_like(mono, -(1 << 31)), mono)    # NaN is minimal (ATen argmin)
     return (mono << 32) | idx.to(torch.int64)
 
 

@@ -1,4 +1,6 @@
 """A/B: CTA-wide tiled backward vs the warp-private variant (vqb_tune bwd_warp)."""
+import os
+os.environ.setdefault("VQB200_EXPERIMENTAL", "1")  # route the ops through libvqb200_bench.so (vqb_tune, microbenchmarks)
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vq_gan_b200 import _cabi, ops

@@ -1,5 +1,7 @@
 """Checks the low-D tensor search (algo 5) against the CUDA-core kernel (algo 1): indices and dmin must be identical."""
 import os
+os.environ.setdefault("VQB200_EXPERIMENTAL", "1")  # route the ops through libvqb200_bench.so (vqb_tune, microbenchmarks)
+import os
 import sys
 
 import torch

@@ -1,3 +1,5 @@
+import os
+os.environ.setdefault("VQB200_EXPERIMENTAL", "1")  # route the ops through libvqb200_bench.so (vqb_tune, microbenchmarks)
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vq_gan_b200 import _cabi, ops
@@ -7,7 +9,7 @@ K = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 _cabi.check(_cabi.lib().vqb_tune(b"tclow_cluster", cl), "vqb_tune")
 dbg = int(os.environ.get("TCLOW_DEBUG", "0"))
 if dbg:
-    _cabi.check(_cabi.lib().vqb_tune(b"tclow_cluster", 16 + dbg), "vqb_tune")
+    _cabi.check(_cabi.lib().vqb_tune(b"tclow_skip_stages", dbg), "vqb_tune")
 torch.manual_seed(0)
 z = torch.randn(B, 4, 32, 32, device="cuda")
 E = torch.randn(K, 4, device="cuda")

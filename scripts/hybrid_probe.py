@@ -1,4 +1,6 @@
 """Feasibility probe: run the CUDA-core search (1 CTA/SM) and the tensor search concurrently on two streams."""
+import os
+os.environ.setdefault("VQB200_EXPERIMENTAL", "1")  # route the ops through libvqb200_bench.so (vqb_tune, microbenchmarks)
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vq_gan_b200 import _cabi, ops
@@ -9,7 +11,7 @@ z = torch.randn(B, D, 32, 32, device="cuda")
 E = torch.randn(K, D, device="cuda")
 i_ref, _, _ = ops.search(z, E, 1)
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
-_cabi.check(lib.vqb_tune(b"lowd_variant", 16 + 1), "tune")
+_cabi.check(lib.vqb_tune(b"lowd_ctas_per_sm", 1), "tune")
 f = float(os.environ.get('FRAC', '0.5'))
 Ba = int(B * f)
 za, zb = z[:Ba].contiguous(), z[Ba:].contiguous()

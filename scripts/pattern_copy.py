@@ -1,4 +1,6 @@
 """Bandwidth ceiling of the NCHW 32-token x strided-channel access pattern used by the tail kernels."""
+import os
+os.environ.setdefault("VQB200_EXPERIMENTAL", "1")  # route the ops through libvqb200_bench.so (vqb_tune, microbenchmarks)
 import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vq_gan_b200 import _cabi

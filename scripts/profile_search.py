@@ -1,4 +1,6 @@
 """Runs only the search op a few times on one workload (short target for `ncu --set full`)."""
+import os
+os.environ.setdefault("VQB200_EXPERIMENTAL", "1")  # route the ops through libvqb200_bench.so (vqb_tune, microbenchmarks)
 import argparse
 import os
 import sys

@@ -1,4 +1,6 @@
 """A/B of the forward-tail / backward kernels: 32-token tiles vs 128-token float4 tiles (vqb_tune tail_tok128)."""
+import os
+os.environ.setdefault("VQB200_EXPERIMENTAL", "1")  # route the ops through libvqb200_bench.so (vqb_tune, microbenchmarks)
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vq_gan_b200 import VectorQuantizer, ops, _cabi

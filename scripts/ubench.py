@@ -1,4 +1,6 @@
 """Times the instruction-mix microbenchmarks of the low-D inner loop (see csrc/vqb_ubench.cu)."""
+import os
+os.environ.setdefault("VQB200_EXPERIMENTAL", "1")  # route the ops through libvqb200_bench.so (vqb_tune, microbenchmarks)
 import ctypes
 import os
 import sys

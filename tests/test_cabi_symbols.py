@@ -12,8 +12,8 @@ from vq_gan_b200 import _cabi
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "vqb200.h")).read()
+def declared_symbols(header="vqb200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     return sorted(set(re.findall(r"VQB_API\s+[\w\s\*]+?\b(vqb_\w+)\s*\(", text)))
 
 
@@ -33,6 +33,20 @@ def test_library_exports_every_declared_symbol():
 
 def test_python_prototypes_cover_header():
     assert sorted(_cabi.PROTOTYPES) == declared_symbols()
+
+
+def test_product_library_has_no_experiment_knobs_or_microbenchmarks():
+    """vqb_tune / vqb_ubench_* / vqb_fma_peak_launch live in the measurement build only
+    (include/vqb200_bench.h, libvqb200_bench.so); the product ABI has no process-global knobs."""
+    handle = ctypes.CDLL(_cabi.LIB_PATH)
+    bench_only = declared_symbols("vqb200_bench.h")
+    assert sorted(bench_only) == sorted(_cabi.BENCH_PROTOTYPES)
+    assert "vqb_tune" in bench_only and "vqb_fma_peak_launch" in bench_only
+    for name in bench_only:
+        assert not hasattr(handle, name), f"{name} must not be exported by libvqb200.so"
+    bench = ctypes.CDLL(_cabi.BENCH_LIB_PATH)
+    for name in bench_only + declared_symbols():
+        assert hasattr(bench, name), f"{name} missing from libvqb200_bench.so"
 
 
 def test_version_and_size_queries_without_gpu():

@@ -80,9 +80,34 @@ def sharded_keys(rank, world):
     return bool(torch.equal(got, want) and int(got.max()) < E.shape[0] // 2)
 
 
+def sharded_keys_nan_code(rank, world):
+    """A NaN code on the LAST shard must win for every finite token, exactly like the unsharded argmin
+    (quantizer.py:76: NaN is minimal), whatever finite scores the other shards report."""
+    from cases import make_case
+    from oracle import vq_oracle as orc
+    from vq_gan_b200 import distributed as vdist
+    c = make_case("small_d8")
+    rows, E = orc.tokens_of(c["z"]), c["E"].clone()
+    nan_code = E.shape[0] - 3
+    E[nan_code, 2] = float("nan")
+    lo, hi = vdist.shard_range(E.shape[0], world, rank)
+    d = orc.distance_matrix(rows, E[lo:hi])
+    idx = torch.argmin(d, dim=1)                       # ATen: first NaN of the shard, else the minimum
+    dmin = d.gather(1, idx[:, None]).squeeze(1)         # NaN where the shard's winner is the NaN code
+    keys = orc.argmin_key(dmin, idx + lo)
+    vdist.reduce_argmin_keys(keys)
+    got = keys & 0xFFFFFFFF
+    want = torch.argmin(orc.distance_matrix(rows, E), dim=1)
+    return bool(torch.equal(got, want) and int(want[0]) == nan_code)
+
+
 def test_dp_stats_allreduce_matches_global_batch():
     assert _run("dp_stats") == {0: True, 1: True}
 
 
 def test_codebook_sharded_min_reduce_matches_global_argmin():
     assert _run("sharded_keys") == {0: True, 1: True}
+
+
+def test_codebook_sharded_nan_code_on_last_shard():
+    assert _run("sharded_keys_nan_code") == {0: True, 1: True}

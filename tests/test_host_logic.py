@@ -79,6 +79,13 @@ def test_quant_conv_is_checkpoint_compatible_with_nn_conv2d():
     assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
     assert all(mine.state_dict()[k].shape == v.shape for k, v in ref.state_dict().items())
     mine.load_state_dict(ref.state_dict(), strict=True)
+    # the reference's own call forms (vq_vae.py:75-76: nn.Conv2d(z_channels, embedding_dim, kernel_size=1))
+    for m in (QuantConv1x1(8, 16, 1), QuantConv1x1(8, 16, kernel_size=1), QuantConv1x1(8, 16, (1, 1), bias=True)):
+        assert m.bias is not None and m.weight.shape == (16, 8, 1, 1)
+    assert QuantConv1x1(8, 16, 1, bias=False).bias is None
+    for bad in (dict(kernel_size=3), dict(stride=2), dict(padding=1)):
+        with pytest.raises(ValueError):
+            QuantConv1x1(8, 16, **bad)
     with pytest.raises(RuntimeError):
         mine(torch.randn(1, 8, 4, 4))
     with pytest.raises(RuntimeError):
@@ -102,3 +109,21 @@ def test_extension_modules_host_contract():
     assert sorted(missing.missing_keys) == ["cluster_size", "embed_sum"] and not missing.unexpected_keys
     with pytest.raises(RuntimeError):
         GraphedVectorQuantizer(plain, torch.randn(1, 8, 4, 4))
+
+
+def test_sharded_argmin_key_orders_like_aten_argmin():
+    """(score, index) keys: signed MIN picks the smallest score, lowest index on ties; NaN is minimal;
+    -0.0 ties with +0.0 (distributed.py:90)."""
+    from oracle import vq_oracle as orc
+    d = torch.tensor([1.5, -2.0, float("nan"), 0.0, -0.0, float("inf"), -float("inf")])
+    idx = torch.arange(7)
+    keys = orc.argmin_key(d, idx)
+    order = torch.argsort(keys).tolist()
+    assert order[0] == 2                      # NaN first
+    assert order[1] == 6                      # then -inf
+    assert order[2] == 1
+    assert order[3:5] == [3, 4]               # +0.0 / -0.0 tie: lower index first
+    assert order[5:] == [0, 5]
+    # two NaN scores on different shards: the lower global index wins
+    k = orc.argmin_key(torch.tensor([float("nan"), float("nan")]), torch.tensor([700, 12]))
+    assert int(k.min() & 0xFFFFFFFF) == 12

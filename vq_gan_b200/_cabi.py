@@ -22,7 +22,6 @@ PROTOTYPES = {
     "vqb_last_error": (c_char_p, []),
     "vqb_device_query": (c_int, [c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                  POINTER(c_size_t)]),
-    "vqb_tune": (c_int, [c_char_p, c_int]),
     "vqb_codebook_pack_bytes": (c_size_t, [c_int, c_int]),
     "vqb_codebook_prepare_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "vqb_search_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64, c_int, c_int]),
@@ -51,12 +50,19 @@ PROTOTYPES = {
     "vqb_conv1x1_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vqb_conv1x1_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p,
                                 c_void_p, c_size_t, c_int, c_void_p]),
+}
+
+# measurement build (include/vqb200_bench.h): everything above plus the experiment knobs / microbenchmarks
+BENCH_LIB_PATH = os.path.join(_PKG, "lib", "libvqb200_bench.so")
+BENCH_PROTOTYPES = {
+    "vqb_tune": (c_int, [c_char_p, c_int]),
     "vqb_ubench_launch": (c_int, [c_int, c_int, c_void_p, c_void_p, POINTER(c_double), c_void_p]),
     "vqb_ubench_copy": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p]),
     "vqb_fma_peak_launch": (c_int, [c_int, c_int, c_void_p, POINTER(c_double), c_void_p]),
 }
 
 _lib = None
+_bench_lib = None
 
 
 class VqbError(RuntimeError):
@@ -71,13 +77,34 @@ def lib() -> ctypes.CDLL:
             raise VqbError(
                 f"{LIB_PATH} not found: build it with `python -m vq_gan_b200._build` "
                 "(nvcc, sm_100a).  vq_gan_b200 has no CPU or eager fallback.")
+        if os.environ.get("VQB200_EXPERIMENTAL") == "1":
+            # A/B scripts only: route the ops through the measurement build so vqb_tune() reaches them
+            _lib = bench_lib()
+            return _lib
         handle = ctypes.CDLL(LIB_PATH)
-        for name, (restype, argtypes) in PROTOTYPES.items():
-            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
-            fn.restype = restype
-            fn.argtypes = argtypes
+        _bind(handle, PROTOTYPES)
         _lib = handle
     return _lib
+
+
+def _bind(handle, prototypes) -> None:
+    for name, (restype, argtypes) in prototypes.items():
+        fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+
+
+def bench_lib() -> ctypes.CDLL:
+    """libvqb200_bench.so (measurement build: vqb_tune, microbenchmarks).  bench.py / scripts only."""
+    global _bench_lib
+    if _bench_lib is None:
+        if not os.path.exists(BENCH_LIB_PATH):
+            raise VqbError(f"{BENCH_LIB_PATH} not found: build it with `python -m vq_gan_b200._build`")
+        handle = ctypes.CDLL(BENCH_LIB_PATH)
+        _bind(handle, PROTOTYPES)
+        _bind(handle, BENCH_PROTOTYPES)
+        _bench_lib = handle
+    return _bench_lib
 
 
 def check(rc: int, what: str) -> None:

@@ -20,17 +20,38 @@ int cuda_fail(cudaError_t e, const char* what) {
     return VQB_ERR_CUDA;
 }
 
-int sm_count() {
-    // immutable per-device capability cache
-    static int cached[64];
+// immutable per-device capability cache (written once per device; racing writers store the same value)
+static int g_sm_cached[64];
+
+int device_ready() {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-    if (cached[dev] == 0) {
-        int n = 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cached[dev] = n;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (dev < 0 || dev >= 64) {
+        set_error("device ordinal %d outside the capability cache (0..63)", dev);
+        return VQB_ERR_UNSUPPORTED;
     }
-    return cached[dev];
+    if (g_sm_cached[dev] == 0) {
+        int n = 0, major = 0;
+        e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(MultiProcessorCount)");
+        e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute(ComputeCapabilityMajor)");
+        if (n <= 0 || major != 10) {
+            set_error("libvqb200 needs an sm_100a device (B200); device %d reports %d SMs, compute capability %d.x", dev, n,
+                      major);
+            return VQB_ERR_UNSUPPORTED;
+        }
+        g_sm_cached[dev] = n;
+    }
+    return VQB_OK;
+}
+
+int sm_count() {
+    // every launching entry point runs VQB_DEVICE_TRY() first, so the cache is filled here
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    return g_sm_cached[dev];
 }
 
 }  // namespace vqb
@@ -62,44 +83,54 @@ extern "C" int vqb_device_query(int device, int* sm, int* cc_major, int* cc_mino
     return VQB_OK;
 }
 
+#ifdef VQB_EXPERIMENTAL
+// measurement build only (libvqb200_bench.so, include/vqb200_bench.h): process-global, not thread-safe
 extern "C" int vqb_tune(const char* key, int value) {
-    if (key && strcmp(key, "lowd_variant") == 0 && ((value >= 0 && value <= 4) || (value >= 16 && value <= 19))) {
+    if (!key) {
+        set_error("vqb_tune: null key");
+        return VQB_ERR_INVALID_ARG;
+    }
+    if (strcmp(key, "lowd_variant") == 0 && value >= 0 && value <= 4) {
         set_lowd_variant(value);
         return VQB_OK;
     }
-    if (key && strcmp(key, "tc16_cluster") == 0 && (value == 1 || value == 2 || value == 4)) {
+    if (strcmp(key, "lowd_ctas_per_sm") == 0 && value >= 0 && value <= 3) {
+        set_lowd_variant(16 + value);
+        return VQB_OK;
+    }
+    if (strcmp(key, "tc16_cluster") == 0 && (value == 1 || value == 2 || value == 4)) {
         set_tc16_cluster(value);
         return VQB_OK;
     }
-    if (key && strcmp(key, "tclow_cluster") == 0 && (value == 1 || value == 2 || value == 4 || (value >= 16 && value < 24))) {
+    if (strcmp(key, "tclow_cluster") == 0 && (value == 1 || value == 2 || value == 4)) {
         set_tclow_cluster(value);
         return VQB_OK;
     }
-    if (key && (strcmp(key, "bwd_pass_channels") == 0 || strcmp(key, "fwd_pass_channels") == 0) &&
+    if (strcmp(key, "tclow_skip_stages") == 0 && value >= 0 && value < 8) {
+        set_tclow_cluster(16 + value);
+        return VQB_OK;
+    }
+    if ((strcmp(key, "bwd_pass_channels") == 0 || strcmp(key, "fwd_pass_channels") == 0) &&
         (value == 64 || value == 128 || value == 192 || value == 256)) {
-        if (key[0] == 'f') value += 1024;
-        set_bwd_pass_cap(value);
+        set_tail_knob(key, value);
         return VQB_OK;
     }
-    if (key && strcmp(key, "bwd_warp") == 0 && value >= 0 && value <= 2) {
-        set_bwd_pass_cap(8192 + value);
+    if ((strcmp(key, "bwd_warp") == 0 || strcmp(key, "tail_warp") == 0) && value >= 0 && value <= 2) {
+        set_tail_knob(key, value);
         return VQB_OK;
     }
-    if (key && strcmp(key, "tail_warp") == 0 && value >= 0 && value <= 2) {
-        set_bwd_pass_cap(4096 + value);
+    if (strcmp(key, "tail_tok128") == 0 && (value == 0 || value == 1)) {
+        set_tail_knob(key, value);
         return VQB_OK;
     }
-    if (key && strcmp(key, "tail_tok128") == 0 && (value == 0 || value == 1)) {
-        set_bwd_pass_cap(2048 + value);
-        return VQB_OK;
-    }
-    if (key && strcmp(key, "conv_debug") == 0 && value >= 0 && value < 16) {
+    if (strcmp(key, "conv_debug") == 0 && value >= 0 && value < 16) {
         set_conv_debug(value);
         return VQB_OK;
     }
-    set_error("vqb_tune: unknown key or value (%s = %d)", key ? key : "(null)", value);
+    set_error("vqb_tune: unknown key or value (%s = %d)", key, value);
     return VQB_ERR_INVALID_ARG;
 }
+#endif
 
 extern "C" size_t vqb_codebook_pack_bytes(int K, int D) {
     if (K <= 0 || D <= 0) return 0;
@@ -108,6 +139,7 @@ extern "C" size_t vqb_codebook_pack_bytes(int K, int D) {
 
 extern "C" int vqb_codebook_prepare_f32(const float* E, int K, int D, void* pack, size_t pack_bytes,
                                         vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (!E || !pack || K <= 0 || D <= 0) {
         set_error("vqb_codebook_prepare_f32: invalid argument (K=%d D=%d)", K, D);
         return VQB_ERR_INVALID_ARG;
@@ -162,6 +194,7 @@ __global__ void write_stats_kernel(int64_t* stats, int64_t rescored, int64_t alg
 extern "C" int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                               const void* pack, int64_t* idx_out, float* dmin_out, void* workspace,
                               size_t workspace_bytes, int algo, int64_t* stats_out, vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (B < 0 || HW < 0 || D <= 0 || K <= 0) {
         set_error("vqb_search_f32: invalid shape B=%lld D=%d HW=%lld K=%d", (long long)B, D, (long long)HW, K);
         return VQB_ERR_INVALID_ARG;

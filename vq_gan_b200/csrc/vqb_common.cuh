@@ -8,6 +8,9 @@
 #include <math.h>
 
 #include "../../include/vqb200.h"
+#ifdef VQB_EXPERIMENTAL
+#include "../../include/vqb200_bench.h"
+#endif
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "libvqb200 is written for sm_100a (B200) only"
@@ -29,7 +32,21 @@ int cuda_fail(cudaError_t e, const char* what);
         if (_e != cudaSuccess) return ::vqb::cuda_fail(_e, what); \
     } while (0)
 
-int sm_count();  // cached per current device
+int device_ready();  // VQB_OK once the current device is a queried sm_100 part, an error code otherwise
+int sm_count();      // SM count of the current device (valid after device_ready())
+#define VQB_DEVICE_TRY()                                  \
+    do {                                                  \
+        if (int _rc = ::vqb::device_ready()) return _rc;  \
+    } while (0)
+
+// Launch-shape knobs.  The product library (libvqb200.so) compiles them as constants: it has no
+// process-global mutable state.  Only the measurement build (libvqb200_bench.so, -DVQB_EXPERIMENTAL,
+// include/vqb200_bench.h) makes them variables behind vqb_tune() for A/B experiments.
+#ifdef VQB_EXPERIMENTAL
+#define VQB_KNOB static int
+#else
+#define VQB_KNOB static constexpr int
+#endif
 
 // ---- packed codebook layout ----------------------------------------------
 // header (int32[64]): [0] first NaN code (K if none) [1] K [2] D [4] float bits of max 0.5|e|^2
@@ -172,9 +189,11 @@ int launch_search_tclow(const float* z, int64_t B, int D, int64_t HW, const floa
 int launch_search_lowd_list(const float* z, int64_t B, int D, int64_t HW, int K, const void* pack,
                             const int32_t* list, const int32_t* list_count, int64_t* idx_out,
                             float* dmin_out, cudaStream_t s);
+#ifdef VQB_EXPERIMENTAL
 void set_tclow_cluster(int c);
-void set_bwd_pass_cap(int c);
+void set_tail_knob(const char* key, int value);
 void set_conv_debug(int v);
+#endif
 size_t search_tc16_workspace_bytes(int64_t n_tokens, int D, int K);
 int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                        const void* pack, int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes,

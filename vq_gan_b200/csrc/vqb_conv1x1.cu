@@ -347,10 +347,12 @@ static bool conv_tc_eligible(int Cin, int Cout) {
 
 using namespace vqb;
 
-static int g_conv_debug = 0;
+VQB_KNOB g_conv_debug = 0;
+#ifdef VQB_EXPERIMENTAL
 namespace vqb {
 void set_conv_debug(int v) { g_conv_debug = v; }
 }
+#endif
 
 extern "C" size_t vqb_conv1x1_workspace_bytes(int Cin, int Cout) {
     if (Cin <= 0 || Cout <= 0) return 0;
@@ -360,6 +362,7 @@ extern "C" size_t vqb_conv1x1_workspace_bytes(int Cin, int Cout) {
 extern "C" int vqb_conv1x1_f32(const float* x, int64_t B, int Cin, int64_t HW, const float* W, const float* bias,
                                int Cout, float* y, void* workspace, size_t workspace_bytes, int algo,
                                vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (B < 0 || HW < 0 || Cin <= 0 || Cout <= 0) {
         set_error("vqb_conv1x1_f32: invalid shape B=%lld Cin=%d HW=%lld Cout=%d", (long long)B, Cin, (long long)HW, Cout);
         return VQB_ERR_INVALID_ARG;

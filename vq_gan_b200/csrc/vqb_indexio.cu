@@ -78,6 +78,7 @@ extern "C" int vqb_index_bytes(int K) { return K <= 0 ? 0 : (K <= 256 ? 1 : (K <
 
 extern "C" int vqb_indices_narrow(const int64_t* idx, int64_t n, int K, void* codes_out, int elem_bytes,
                                   int* err_flag, vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (n < 0 || K <= 0 || (elem_bytes != 1 && elem_bytes != 2 && elem_bytes != 4) || elem_bytes < vqb_index_bytes(K)) {
         set_error("vqb_indices_narrow: invalid argument (n=%lld K=%d elem_bytes=%d)", (long long)n, K, elem_bytes);
         return VQB_ERR_INVALID_ARG;
@@ -100,6 +101,7 @@ extern "C" int vqb_indices_narrow(const int64_t* idx, int64_t n, int K, void* co
 }
 
 extern "C" int vqb_indices_widen(const void* codes, int64_t n, int elem_bytes, int64_t* idx_out, vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (n < 0 || (elem_bytes != 1 && elem_bytes != 2 && elem_bytes != 4)) {
         set_error("vqb_indices_widen: invalid argument (n=%lld elem_bytes=%d)", (long long)n, elem_bytes);
         return VQB_ERR_INVALID_ARG;

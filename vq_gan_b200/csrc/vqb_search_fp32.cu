@@ -187,9 +187,13 @@ __global__ void __launch_bounds__(kFtThreads, 2)
                     atomicMin(keys + (m0 + row), score_key(best[i], bidx[i]));
                 } else {
                     int r = bidx[i];
-                    if (first_nan < K) r = (best[i] == INFINITY) ? 0 : first_nan;
+                    float dm = best[i];
+                    if (first_nan < K) {
+                        r = (best[i] == INFINITY) ? 0 : first_nan;
+                        if (best[i] != INFINITY) dm = __int_as_float(0x7fc00000);  // the NaN code's score
+                    }
                     idx_out[t] = r;
-                    if (dmin_out) dmin_out[t] = best[i];
+                    if (dmin_out) dmin_out[t] = dm;
                 }
             }
         }
@@ -209,7 +213,10 @@ __global__ void __launch_bounds__(256)
         float d;
         int idx;
         key_unpack(keys[r], d, idx);
-        if (first_nan < K) idx = (d == INFINITY) ? 0 : first_nan;
+        if (first_nan < K) {
+            idx = (d == INFINITY) ? 0 : first_nan;
+            if (d != INFINITY) d = __int_as_float(0x7fc00000);  // the NaN code's score
+        }
         idx_out[t] = idx;
         if (dmin_out) dmin_out[t] = d;
     }

@@ -46,11 +46,13 @@ struct LowDCfg {
     static constexpr size_t kSmemBytes = 2 * sizeof(float) * kTileFloats + 64;
 };
 
-static int g_lowd_variant = 0;
-static int g_lowd_ctas_per_sm = 0;  // 0 = the variant's own residency; 1 leaves room for a co-running kernel
+VQB_KNOB g_lowd_variant = 0;
+VQB_KNOB g_lowd_ctas_per_sm = 0;  // 0 = the variant's own residency; 1 leaves room for a co-running kernel
+#ifdef VQB_EXPERIMENTAL
 void set_lowd_variant(int v) {
     if (v >= 16) g_lowd_ctas_per_sm = v - 16; else g_lowd_variant = v;
 }
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -263,9 +265,15 @@ __device__ __forceinline__ void lowd_segment(LowDCtx<D, V>& c, int64_t seg_base)
     for (int t = 0; t < T; ++t) {
         if (tok[t] >= 0) {
             int r = best[t];
-            if (c.first_nan < c.K) r = (m[t] == INFINITY) ? 0 : c.first_nan;  // NaN code is minimal
+            float dm = m[t];
+            if (c.first_nan < c.K && m[t] != INFINITY) {  // NaN code is minimal, and so is its score (sharded MIN keys)
+                r = c.first_nan;
+                dm = __int_as_float(0x7fc00000);
+            } else if (c.first_nan < c.K) {
+                r = 0;
+            }
             c.idx_out[tok[t]] = r;
-            if (c.dmin_out) c.dmin_out[tok[t]] = m[t];
+            if (c.dmin_out) c.dmin_out[tok[t]] = dm;
         }
     }
 }

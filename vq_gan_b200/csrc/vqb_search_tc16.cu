@@ -694,8 +694,10 @@ size_t search_tc16_workspace_bytes(int64_t n_tokens, int D, int K) {
     return t16_workspace(n_tokens, D).total;
 }
 
-static int g_tc16_cluster = 2;
+VQB_KNOB g_tc16_cluster = 2;
+#ifdef VQB_EXPERIMENTAL
 void set_tc16_cluster(int c) { g_tc16_cluster = c; }
+#endif
 
 template <int NKB, int CL>
 static int launch_tc16_cl(const CUtensorMap& mz, const CUtensorMap& me, const T16Params& p, cudaStream_t s) {

@@ -453,11 +453,13 @@ size_t search_tclow_workspace_bytes(int64_t n_tokens, int D, int K) {
     return low_workspace(n_tokens, D).total;
 }
 
-static int g_tclow_cluster = 2;
-static int g_tclow_debug = 0;  // bit 0: skip the tensor kernel, bit 1: skip the chunk re-score, bit 2: skip the list search
+VQB_KNOB g_tclow_cluster = 2;
+VQB_KNOB g_tclow_debug = 0;  // bit 0: skip the tensor kernel, bit 1: skip the chunk re-score, bit 2: skip the list search
+#ifdef VQB_EXPERIMENTAL
 void set_tclow_cluster(int c) {
     if (c >= 16) g_tclow_debug = c - 16; else g_tclow_cluster = c;
 }
+#endif
 
 template <int CL>
 static int launch_tclow_cl(const LowParams& p0, cudaStream_t s) {

@@ -50,6 +50,7 @@ using namespace vqb;
 
 extern "C" int vqb_stats_pack(const float* dE, int64_t n_dE, const float* scalars, int n_scalars, const int64_t* hist,
                               int n_hist, float* flat_out, vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (n_dE < 0 || n_scalars < 0 || n_hist < 0 || (n_dE && !dE) || (n_scalars && !scalars) || (n_hist && !hist) || !flat_out) {
         set_error("vqb_stats_pack: invalid argument");
         return VQB_ERR_INVALID_ARG;
@@ -66,6 +67,7 @@ extern "C" int vqb_stats_pack(const float* dE, int64_t n_dE, const float* scalar
 
 extern "C" int vqb_stats_unpack(const float* flat, int64_t n_dE, int n_scalars, int n_hist, float dE_scale, float* dE_out,
                                 float* scalars_out, int64_t* hist_out, vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (n_dE < 0 || n_scalars < 0 || n_hist < 0 || !flat || (n_dE && !dE_out) || (n_scalars && !scalars_out) ||
         (n_hist && !hist_out)) {
         set_error("vqb_stats_unpack: invalid argument");

@@ -873,17 +873,26 @@ __global__ void __launch_bounds__(kTailThreads)
     }
 }
 
-__global__ void ema_sizes_kernel(float* __restrict__ cluster_size, const float* __restrict__ counts,
-                                 int K, float decay, float* __restrict__ total) {
-    float part = 0.f;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+// ONE block, fixed summation order (fp64 per thread over a fixed stride, then a fixed tree): the total -- and with
+// it the Laplace-smoothed update -- is bit-identical from run to run and from rank to rank
+__global__ void __launch_bounds__(1024) ema_sizes_kernel(float* __restrict__ cluster_size,
+                                                         const float* __restrict__ counts, int K, float decay,
+                                                         float* __restrict__ total) {
+    __shared__ double part_s[32];
+    double part = 0.0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
         const float v = cluster_size[k] * decay + counts[k] * (1.f - decay);
         cluster_size[k] = v;
-        part += v;
+        part += (double)v;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(total, part);
+    part = warp_sum_f64(part);
+    if ((threadIdx.x & 31) == 0) part_s[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? part_s[threadIdx.x] : 0.0;
+        v = warp_sum_f64(v);
+        if (threadIdx.x == 0) *total = (float)v;
+    }
 }
 
 __global__ void ema_embed_kernel(float* __restrict__ E, const float* __restrict__ cluster_size,
@@ -905,8 +914,11 @@ __global__ void pack_keys_kernel(const float* __restrict__ dmin, const int64_t* 
                                  int64_t n, int64_t index_offset, int64_t* __restrict__ keys) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int bits = __float_as_int(dmin[i]);
-    if (bits < 0) bits ^= 0x7fffffff;  // monotone signed order of IEEE floats
+    // ATen's argmin treats NaN as minimal (quantizer.py:76): a NaN score packs as the smallest key, so the MIN over
+    // shards picks the NaN with the lowest global index; -0.0 is canonicalised to +0.0 (equal scores must tie)
+    const float dv = dmin[i];
+    int bits = (dv != dv) ? (int)0x80000000 : __float_as_int(dv + 0.f);
+    if (bits < 0 && dv == dv) bits ^= 0x7fffffff;  // monotone signed order of IEEE floats
     keys[i] = ((int64_t)bits << 32) | (int64_t)(uint32_t)(idx[i] + index_offset);
 }
 
@@ -918,47 +930,9 @@ __global__ void unpack_keys_kernel(const int64_t* __restrict__ keys, int64_t n,
     idx_out[i] = (int64_t)(uint32_t)(key & 0xffffffffll);
     if (dmin_out) {
         int bits = (int)(key >> 32);
-        if (bits < 0) bits ^= 0x7fffffff;
+        if (bits == (int)0x80000000) bits = 0x7fc00000;  // the NaN sentinel of pack_keys_kernel
+        else if (bits < 0) bits ^= 0x7fffffff;
         dmin_out[i] = __int_as_float(bits);
-    }
-}
-
-// FP32 FMA peak: 16 independent chains per thread, operands from registers
-template <bool kPacked>
-__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float a, float b, float* sink) {
-    if constexpr (kPacked) {
-        unsigned long long x[8];
-        const unsigned long long a2 = pack_f32x2(a, a + 1e-3f), b2 = pack_f32x2(b, b - 1e-3f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = pack_f32x2(threadIdx.x * 1e-3f + i, i * 0.5f);
-        for (int it = 0; it < iters; ++it) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = fma_f32x2(x[i], a2, b2);
-        }
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float lo, hi;
-            unpack_f32x2(x[i], lo, hi);
-            s += lo + hi;
-        }
-        if (s == 123.456f) sink[0] = s;
-    } else {
-        float x[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = threadIdx.x * 1e-3f + i;
-        for (int it = 0; it < iters; ++it) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = fmaf(x[i], a, b);
-        }
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) s += x[i];
-        if (s == 123.456f) sink[0] = s;
     }
 }
 
@@ -981,20 +955,22 @@ static int check_shape(int64_t B, int D, int64_t HW, int K) {
     return VQB_OK;
 }
 
-static int g_bwd_pass_cap = 64;   // measured best on B200 (profiles/r01_tail_pass_width_sweep.txt)
-static int g_fwd_pass_cap = 64;
-static int g_bwd_warp = 0;    // warp-private backward (vqb_tune "bwd_warp")
-static int g_tail_warp = 1;   // warp-private forward tail (vqb_tune "tail_warp": 0 off, 1 auto = D >= 128, 2 force)
-static int g_tail_tok128 = 1;  // 128-token float4 kernels when the layout allows (vqb_tune "tail_tok128", 0 = off)
+VQB_KNOB g_bwd_pass_cap = 64;   // measured best on B200 (profiles/r01_tail_pass_width_sweep.txt)
+VQB_KNOB g_fwd_pass_cap = 64;
+VQB_KNOB g_bwd_warp = 0;    // warp-private backward (vqb_tune "bwd_warp")
+VQB_KNOB g_tail_warp = 1;   // warp-private forward tail (vqb_tune "tail_warp": 0 off, 1 auto = D >= 128, 2 force)
+VQB_KNOB g_tail_tok128 = 1;  // 128-token float4 kernels when the layout allows (vqb_tune "tail_tok128", 0 = off)
+#ifdef VQB_EXPERIMENTAL
 namespace vqb {
-void set_bwd_pass_cap(int c) {
-    if (c >= 8192) g_bwd_warp = c - 8192;
-    else if (c >= 4096) g_tail_warp = c - 4096;
-    else if (c >= 2048) g_tail_tok128 = c - 2048;
-    else if (c >= 1024) g_fwd_pass_cap = c - 1024;
-    else g_bwd_pass_cap = c;
+void set_tail_knob(const char* key, int value) {
+    if (key[0] == 'b' && key[4] == 'p') g_bwd_pass_cap = value;       // bwd_pass_channels
+    else if (key[0] == 'f') g_fwd_pass_cap = value;                   // fwd_pass_channels
+    else if (key[0] == 'b') g_bwd_warp = value;                       // bwd_warp
+    else if (key[5] == 'w') g_tail_warp = value;                      // tail_warp
+    else g_tail_tok128 = value;                                       // tail_tok128
 }
 }  // namespace vqb
+#endif
 
 extern "C" size_t vqb_tail_partials_bytes(int64_t n_tokens) {
     return sizeof(double) * (size_t)((n_tokens + 31) / 32 + 1);
@@ -1004,6 +980,7 @@ extern "C" int vqb_gather_loss_st_f32(const float* z, const float* E, const int6
                                       int D, int64_t HW, int K, float beta, float* zq_out,
                                       float* loss_out, void* partials, size_t partials_bytes,
                                       int* err_flag, vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (int rc = check_shape(B, D, HW, K)) return rc;
     if (!z || !E || !idx || !zq_out || !loss_out || !partials) {
         set_error("vqb_gather_loss_st_f32: null pointer");
@@ -1091,6 +1068,7 @@ extern "C" int vqb_backward_f32(const float* z, const float* E, const int64_t* i
                                 const float* g_vq, float beta, int64_t B, int D, int64_t HW, int K,
                                 float* dz_out, float* dE_accum, int64_t* hist_accum,
                                 vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (int rc = check_shape(B, D, HW, K)) return rc;
     if (!z || !E || !idx || !dz_out) {
         set_error("vqb_backward_f32: null pointer");
@@ -1153,6 +1131,7 @@ extern "C" int vqb_backward_f32(const float* z, const float* E, const int64_t* i
 
 extern "C" int vqb_gather_f32(const float* E, const int64_t* idx, int64_t B, int D, int64_t HW, int K,
                               float* out, int* err_flag, vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (int rc = check_shape(B, D, HW, K)) return rc;
     if (!E || !idx || !out) {
         set_error("vqb_gather_f32: null pointer");
@@ -1176,6 +1155,7 @@ extern "C" int vqb_gather_f32(const float* E, const int64_t* idx, int64_t B, int
 
 extern "C" int vqb_hist_i64(const int64_t* idx, int64_t n_tokens, int K, int64_t* hist_out,
                             int64_t* used_out, int* err_flag, vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (n_tokens < 0 || K <= 0 || !hist_out || (!idx && n_tokens > 0)) {
         set_error("vqb_hist_i64: invalid argument");
         return VQB_ERR_INVALID_ARG;
@@ -1202,6 +1182,7 @@ extern "C" int vqb_hist_i64(const int64_t* idx, int64_t n_tokens, int K, int64_t
 
 extern "C" int vqb_code_sums_f32(const float* z, const int64_t* idx, int64_t B, int D, int64_t HW, int K,
                                  float* counts_accum, float* sums_accum, vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (int rc = check_shape(B, D, HW, K)) return rc;
     if (!z || !idx || !counts_accum || !sums_accum) {
         set_error("vqb_code_sums_f32: null pointer");
@@ -1226,15 +1207,13 @@ extern "C" int vqb_code_sums_f32(const float* z, const int64_t* idx, int64_t B, 
 extern "C" int vqb_ema_update_f32(float* E, float* cluster_size, float* embed_sum, const float* counts,
                                   const float* sums, int K, int D, float decay, float eps,
                                   float* total_scratch, vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (K <= 0 || D <= 0 || !E || !cluster_size || !embed_sum || !counts || !sums || !total_scratch) {
         set_error("vqb_ema_update_f32: invalid argument");
         return VQB_ERR_INVALID_ARG;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    VQB_CUDA_TRY(cudaMemsetAsync(total_scratch, 0, sizeof(float), s));
-    int blocks = (K + 255) / 256;
-    if (blocks > 1024) blocks = 1024;
-    ema_sizes_kernel<<<blocks, 256, 0, s>>>(cluster_size, counts, K, decay, total_scratch);
+    ema_sizes_kernel<<<1, 1024, 0, s>>>(cluster_size, counts, K, decay, total_scratch);
     VQB_LAUNCH_CHECK("ema_sizes_kernel");
     size_t n = (size_t)K * D;
     size_t b2 = (n + 255) / 256;
@@ -1247,6 +1226,7 @@ extern "C" int vqb_ema_update_f32(float* E, float* cluster_size, float* embed_su
 
 extern "C" int vqb_pack_argmin_keys(const float* dmin, const int64_t* idx, int64_t n,
                                     int64_t index_offset, int64_t* keys_out, vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (n < 0 || (n > 0 && (!dmin || !idx || !keys_out))) {
         set_error("vqb_pack_argmin_keys: invalid argument");
         return VQB_ERR_INVALID_ARG;
@@ -1260,6 +1240,7 @@ extern "C" int vqb_pack_argmin_keys(const float* dmin, const int64_t* idx, int64
 
 extern "C" int vqb_unpack_argmin_keys(const int64_t* keys, int64_t n, int64_t* idx_out, float* dmin_out,
                                       vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (n < 0 || (n > 0 && (!keys || !idx_out))) {
         set_error("vqb_unpack_argmin_keys: invalid argument");
         return VQB_ERR_INVALID_ARG;
@@ -1268,23 +1249,5 @@ extern "C" int vqb_unpack_argmin_keys(const int64_t* keys, int64_t n, int64_t* i
     unpack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         keys, n, idx_out, dmin_out);
     VQB_LAUNCH_CHECK("unpack_keys_kernel");
-    return VQB_OK;
-}
-
-extern "C" int vqb_fma_peak_launch(int packed, int iters, float* sink, double* flops_host,
-                                   vqb_stream_t stream) {
-    if (iters <= 0 || !sink) {
-        set_error("vqb_fma_peak_launch: invalid argument");
-        return VQB_ERR_INVALID_ARG;
-    }
-    const int blocks = sm_count() * 8;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (packed)
-        fma_peak_kernel<true><<<blocks, 256, 0, s>>>(iters, 0.999f, 0.001f, sink);
-    else
-        fma_peak_kernel<false><<<blocks, 256, 0, s>>>(iters, 0.999f, 0.001f, sink);
-    VQB_LAUNCH_CHECK("fma_peak_kernel");
-    // per thread per iteration: 8 rounds x 16 lanes of FMA = 128 FMA = 256 flop
-    if (flops_host) *flops_host = 256.0 * iters * 256.0 * blocks;
     return VQB_OK;
 }

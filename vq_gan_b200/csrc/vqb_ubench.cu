@@ -184,6 +184,7 @@ using namespace vqb;
 
 extern "C" int vqb_ubench_copy(const float* a, const float* b, float* out, int64_t B, int D, int64_t HW, int mode,
                                vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (!a || !out || ((mode == 1 || mode == 4) && !b) || B <= 0 || D <= 0 || D % 64 != 0 || HW <= 0 || HW % 4 != 0 || mode < 0 ||
         mode > 4) {
         set_error("vqb_ubench_copy: invalid argument");
@@ -199,6 +200,7 @@ extern "C" int vqb_ubench_copy(const float* a, const float* b, float* out, int64
 
 extern "C" int vqb_ubench_launch(int mode, int sweeps, const float* src, float* sink, double* flops_host,
                                  vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
     if (mode < 0 || mode > 5 || sweeps <= 0 || !src || !sink) {
         set_error("vqb_ubench_launch: invalid argument");
         return VQB_ERR_INVALID_ARG;
@@ -216,5 +218,63 @@ extern "C" int vqb_ubench_launch(int mode, int sweeps, const float* src, float* 
     }
     VQB_LAUNCH_CHECK("ubench_kernel");
     if (flops_host) *flops_host = 2.0 * 4 * (double)blocks * 256 * T * kUbCodes * sweeps;
+    return VQB_OK;
+}
+
+// FP32 FMA peak: 16 independent chains per thread, operands from registers
+template <bool kPacked>
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float a, float b, float* sink) {
+    if constexpr (kPacked) {
+        unsigned long long x[8];
+        const unsigned long long a2 = pack_f32x2(a, a + 1e-3f), b2 = pack_f32x2(b, b - 1e-3f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = pack_f32x2(threadIdx.x * 1e-3f + i, i * 0.5f);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = fma_f32x2(x[i], a2, b2);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float lo, hi;
+            unpack_f32x2(x[i], lo, hi);
+            s += lo + hi;
+        }
+        if (s == 123.456f) sink[0] = s;
+    } else {
+        float x[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = threadIdx.x * 1e-3f + i;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = fmaf(x[i], a, b);
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += x[i];
+        if (s == 123.456f) sink[0] = s;
+    }
+}
+
+extern "C" int vqb_fma_peak_launch(int packed, int iters, float* sink, double* flops_host,
+                                   vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
+    if (iters <= 0 || !sink) {
+        set_error("vqb_fma_peak_launch: invalid argument");
+        return VQB_ERR_INVALID_ARG;
+    }
+    const int blocks = sm_count() * 8;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (packed)
+        fma_peak_kernel<true><<<blocks, 256, 0, s>>>(iters, 0.999f, 0.001f, sink);
+    else
+        fma_peak_kernel<false><<<blocks, 256, 0, s>>>(iters, 0.999f, 0.001f, sink);
+    VQB_LAUNCH_CHECK("fma_peak_kernel");
+    // per thread per iteration: 8 rounds x 16 lanes of FMA = 128 FMA = 256 flop
+    if (flops_host) *flops_host = 256.0 * iters * 256.0 * blocks;
     return VQB_OK;
 }

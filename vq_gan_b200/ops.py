@@ -232,6 +232,10 @@ def _quantize_setup(ctx, inputs, output):
     z, weight, beta, _algo = inputs
     ctx.save_for_backward(z, weight, output[3])
     ctx.beta = beta
+    # only z_q and vq_loss carry gradient.  `mse` is the LOGGED value of codebook_loss / commitment_loss (the
+    # reference returns them as Python floats, quantizer.py:106-107): a loss built from it must raise instead
+    # of silently receiving zero gradients
+    ctx.mark_non_differentiable(output[2], output[3], output[4])
 
 
 def _quantize_bwd(ctx, g_zq, g_vq, g_mse, g_idx, g_stats):
@@ -533,10 +537,11 @@ def fma_peak_tflops(packed: bool, iters: int = 4096, repeats: int = 5) -> float:
     sink = torch.zeros(1, dtype=torch.float32, device="cuda")
     flops = ctypes.c_double(0.0)
     best = 0.0
+    blib = _cabi.bench_lib()  # measurement build; the product library carries no microbenchmarks
     for _ in range(repeats + 1):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        check(lib().vqb_fma_peak_launch(int(packed), iters, _p(sink), ctypes.byref(flops), _stream()),
+        check(blib.vqb_fma_peak_launch(int(packed), iters, _p(sink), ctypes.byref(flops), _stream()),
               "vqb_fma_peak_launch")
         b.record()
         b.synchronize()

@@ -119,8 +119,16 @@ class QuantConv1x1(nn.Conv2d):
     (3xTF32 tcgen05 when cin % 32 == 0, cout % 16 == 0, cout <= 256; CUDA cores otherwise); the weight
     gradient is a library GEMM."""
 
-    def __init__(self, in_channels: int, out_channels: int, bias: bool = True, *, algo: int = 0):
-        super().__init__(in_channels, out_channels, kernel_size=1, bias=bias)
+    def __init__(self, in_channels: int, out_channels: int, kernel_size=1, stride=1, padding=0, bias: bool = True, *,
+                 algo: int = 0):
+        # same positional order as nn.Conv2d, so the reference's calls `nn.Conv2d(z_channels, embedding_dim,
+        # kernel_size=1)` (vq_vae.py:75-76) and `nn.Conv2d(cin, cout, 1)` become a rename
+        def _one(v, want):
+            return all(int(x) == want for x in (v if isinstance(v, (tuple, list)) else (v,)))
+        if not (_one(kernel_size, 1) and _one(stride, 1) and _one(padding, 0)):
+            raise ValueError(f"QuantConv1x1 is a 1x1 convolution: kernel_size=1, stride=1, padding=0 "
+                             f"(got {kernel_size}, {stride}, {padding})")
+        super().__init__(in_channels, out_channels, kernel_size=1, bias=bool(bias))
         self.algo = algo
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -171,9 +179,10 @@ class EMAVectorQuantizer(VectorQuantizer):
                 counts, sums = ops.code_sums(z.detach(), indices, self.num_embeddings)
                 if torch.distributed.is_available() and torch.distributed.is_initialized() \
                         and torch.distributed.get_world_size() > 1:
-                    flat = torch.cat([counts, sums.reshape(-1)])
+                    # ONE message [sums | counts] through the packed-statistics kernels of the data-parallel path
+                    flat = ops.stats_pack(sums, None, counts)
                     torch.distributed.all_reduce(flat)
-                    counts, sums = flat[:self.num_embeddings], flat[self.num_embeddings:].reshape(sums.shape)
+                    sums, counts, _ = ops.stats_unpack(flat, sums.shape, self.num_embeddings, 0, 1.0)
                 ops.ema_update(self.embedding.weight.data, self.cluster_size, self.embed_sum, counts.contiguous(),
                                sums.contiguous(), float(self.decay), float(self.eps))
         m = mse.detach() if self.lazy_stats else mse.item()
