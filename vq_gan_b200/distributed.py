@@ -29,6 +29,43 @@ def shard_range(total: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def pin_rank_to_gpu_cores(local_rank: int, ranks_on_node: int, device_index: Optional[int] = None) -> Optional[list]:
+    """Pins this process to its own slice of the CPU cores NVML reports as local to its GPU (same NUMA
+    node / PCIe root).  One process per GPU on an 8-GPU box otherwise lets the scheduler stack several
+    ranks on the same cores and allocate pinned staging buffers on the remote socket; the host side of a
+    step (kernel launches, the per-forward loss read-back of quantizer.py:106-107, H2D of the next batch)
+    then dominates the end-to-end time (SCALE_r01: device-timed efficiency 0.97, end to end 0.65 at N=4).
+    Returns the core list, or None when NVML / sched_setaffinity is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank if device_index is None else device_index)
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        local = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1 and 64 * w + b < ncpu]
+        allowed = sorted(set(local) & set(os.sched_getaffinity(0))) or sorted(os.sched_getaffinity(0))
+        # GPUs that share this core set split it evenly, in local-rank order
+        peers = []
+        for r in range(ranks_on_node):
+            try:
+                m = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(r), words)
+            except Exception:
+                continue
+            if list(m) == list(mask):
+                peers.append(r)
+        if local_rank not in peers:
+            peers = [local_rank]
+        per = max(len(allowed) // len(peers), 1)
+        k = peers.index(local_rank)
+        mine = allowed[k * per:(k + 1) * per] or allowed
+        os.sched_setaffinity(0, mine)
+        return mine
+    except Exception:
+        return None
+
+
 def pack_stats(dE: torch.Tensor, hist: Optional[torch.Tensor], scalars: Optional[torch.Tensor]
                ) -> torch.Tensor:
     """[dE | scalars | hist mod R | hist div R] as one flat fp32 buffer."""
@@ -99,8 +136,31 @@ def sharded_search(z: torch.Tensor, weight_shard: torch.Tensor, index_offset: in
     return ops.unpack_argmin_keys(keys)
 
 
+def _gloo(group) -> bool:
+    return dist.get_backend(group) == "gloo"
+
+
+def _all_gather_rows(out: torch.Tensor, inp: torch.Tensor, group, async_op: bool):
+    """all_gather_into_tensor; on gloo (CPU tests, two ranks sharing one GPU) CUDA tensors go through the
+    list form, which that backend implements for both device types."""
+    if _gloo(group) and inp.is_cuda:
+        dist.all_gather(list(out.chunk(dist.get_world_size(group), dim=0)), inp, group=group)
+        return None
+    return dist.all_gather_into_tensor(out, inp, group=group, async_op=async_op)
+
+
+def _reduce_scatter_min(out: torch.Tensor, keys: torch.Tensor, group, async_op: bool):
+    """MIN reduce-scatter of packed keys; gloo has no CUDA reduce-scatter: MIN all-reduce + own slice."""
+    if _gloo(group) and keys.is_cuda:
+        dist.all_reduce(keys, op=dist.ReduceOp.MIN, group=group)
+        n = out.shape[0]
+        out.copy_(keys[dist.get_rank(group) * n:(dist.get_rank(group) + 1) * n])
+        return None
+    return dist.reduce_scatter_tensor(out, keys, op=dist.ReduceOp.MIN, group=group, async_op=async_op)
+
+
 def sharded_search_dp(z_local: torch.Tensor, weight_shard: torch.Tensor, index_offset: int, group=None,
-                      algo: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                      algo: int = 0, chunks: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """Codebook-sharded search when every rank holds DIFFERENT tokens (bulk encode,
     `preprocess_latents.py`-style loop with `VQVAE.encode_to_indices`):
 
@@ -108,15 +168,42 @@ def sharded_search_dp(z_local: torch.Tensor, weight_shard: torch.Tensor, index_o
       2. local search of this rank's codebook rows for all R*B_r*HW tokens
       3. pack (score, global index) keys, MIN reduce-scatter so each rank receives the
          winners of its own tokens only
-    Every rank must pass the same B_r.  Returns (global indices, min score) of the local tokens."""
+
+    The batch is cut into `chunks` slices of images (0 = auto: about 64K gathered tokens per slice, at most
+    4) and pipelined: every slice's all-gather is issued up front on the communicator's stream, the search
+    of slice c starts as soon as ITS gather has landed while the gathers of slices c+1.. are still in
+    flight over NVLink, and each slice's key reduce-scatter overlaps the next slice's search.  The codebook
+    shard is packed once per call.  Every rank must pass the same B_r.  Returns (global indices, min score)
+    of the local tokens."""
     from . import ops
     world = dist.get_world_size(group)
     z_local = z_local.contiguous()
-    gathered = torch.empty((world * z_local.shape[0],) + tuple(z_local.shape[1:]), dtype=z_local.dtype,
-                           device=z_local.device)
-    dist.all_gather_into_tensor(gathered, z_local, group=group)
-    idx, dmin, _ = ops.search(gathered, weight_shard, algo)
-    keys = ops.pack_argmin_keys(dmin, idx, int(index_offset))
-    mine = torch.empty((z_local.shape[0],) + tuple(keys.shape[1:]), dtype=torch.int64, device=keys.device)
-    dist.reduce_scatter_tensor(mine, keys, op=dist.ReduceOp.MIN, group=group)
+    Bl = int(z_local.shape[0])
+    tok_per_img = 1
+    for d in z_local.shape[2:]:
+        tok_per_img *= int(d)
+    if chunks <= 0:
+        chunks = max(1, min(4, (Bl * tok_per_img * world) // 65536))
+    chunks = max(1, min(chunks, Bl))
+    bounds = [shard_range(Bl, chunks, c) for c in range(chunks)]
+    pack = ops.prepare_codebook(weight_shard) if z_local.is_cuda else None
+    rest = tuple(z_local.shape[1:])
+    gathered, gworks = [], []
+    for lo, hi in bounds:
+        buf = torch.empty((world * (hi - lo),) + rest, dtype=z_local.dtype, device=z_local.device)
+        gworks.append(_all_gather_rows(buf, z_local[lo:hi], group, async_op=True))
+        gathered.append(buf)
+    outs, rworks = [], []
+    for c, (lo, hi) in enumerate(bounds):
+        if gworks[c] is not None:
+            gworks[c].wait()  # the compute stream waits for THIS slice only
+        idx, dmin, _ = ops.search(gathered[c], weight_shard, algo, pack)
+        keys = ops.pack_argmin_keys(dmin, idx, int(index_offset))
+        mine = torch.empty((hi - lo,) + tuple(keys.shape[1:]), dtype=torch.int64, device=keys.device)
+        rworks.append(_reduce_scatter_min(mine, keys, group, async_op=True))
+        outs.append(mine)
+    for w in rworks:
+        if w is not None:
+            w.wait()
+    mine = outs[0] if chunks == 1 else torch.cat(outs, dim=0)
     return ops.unpack_argmin_keys(mine)

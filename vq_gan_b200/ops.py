@@ -94,10 +94,22 @@ def _prepare(weight: Tensor) -> Tensor:
     return pack
 
 
-def _search_into(z: Tensor, weight: Tensor, algo: int, want_dmin: bool):
+def prepare_codebook(weight: Tensor) -> Tensor:
+    """The packed codebook (`vqb_codebook_prepare_f32`) as an opaque uint8 tensor, for callers that search
+    the SAME codebook several times (bulk encode: `search(z, weight, algo, pack)`).  It must be rebuilt
+    whenever `weight` changes; `search` re-checks shape and device only."""
+    _need_cuda_f32(weight, "weight")
+    with _on(weight.device):
+        return _prepare(weight.contiguous())
+
+
+def _search_into(z: Tensor, weight: Tensor, algo: int, want_dmin: bool, pack: Optional[Tensor] = None):
     B, D, HW, K = _shape_bdhw(z, weight)
     dev = z.device
-    pack = _prepare(weight)
+    if pack is None:
+        pack = _prepare(weight)
+    elif pack.device != dev or pack.dtype != torch.uint8 or pack.numel() < lib().vqb_codebook_pack_bytes(K, D):
+        raise RuntimeError("search: `pack` does not belong to this codebook (wrong device, dtype or size)")
     idx = torch.empty((B,) + tuple(z.shape[2:]), dtype=torch.int64, device=dev)
     dmin = torch.empty(idx.shape, dtype=torch.float32, device=dev) if want_dmin else None
     stats = torch.empty(4, dtype=torch.int64, device=dev)  # every search path writes all four entries
@@ -120,8 +132,9 @@ def _search_into(z: Tensor, weight: Tensor, algo: int, want_dmin: bool):
 # search only (encode_to_indices-style bulk use; quantizer.py:68-76)
 # ---------------------------------------------------------------------------
 @torch.library.custom_op("vqb200::search", mutates_args=())
-def search(z: Tensor, weight: Tensor, algo: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
-    """(indices[B,*spatial] int64, dmin[B,*spatial] f32, stats int64[4])."""
+def search(z: Tensor, weight: Tensor, algo: int = 0, pack: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """(indices[B,*spatial] int64, dmin[B,*spatial] f32, stats int64[4]).  `pack`: optional result of
+    `prepare_codebook(weight)` to skip the per-call codebook pre-pass."""
     _need_cuda_f32(z, "z")
     _need_cuda_f32(weight, "weight")
     z = z.contiguous()
@@ -133,12 +146,12 @@ def search(z: Tensor, weight: Tensor, algo: int = 0) -> Tuple[Tensor, Tensor, Te
                 torch.empty(shape, dtype=torch.float32, device=z.device),
                 torch.zeros(4, dtype=torch.int64, device=z.device))
     with _on(z.device):
-        idx, dmin, stats = _search_into(z, weight, algo, True)
+        idx, dmin, stats = _search_into(z, weight, algo, True, pack)
     return idx, dmin, stats
 
 
 @search.register_fake
-def _(z, weight, algo=0):
+def _(z, weight, algo=0, pack=None):
     shape = (z.shape[0],) + tuple(z.shape[2:])
     return (z.new_empty(shape, dtype=torch.int64), z.new_empty(shape),
             z.new_empty((4,), dtype=torch.int64))

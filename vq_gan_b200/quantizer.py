@@ -48,6 +48,7 @@ class VectorQuantizer(nn.Module):
         self.embedding = nn.Embedding(num_embeddings, embedding_dim)
         self.embedding.weight.data.uniform_(-1.0 / num_embeddings, 1.0 / num_embeddings)
         self.last_search_stats = None  # int64[4] device tensor of the last forward
+        self.last_mse = None           # 0-dim device tensor: codebook_loss of the last forward
 
     # -- forward (quantizer.py:50-110) ---------------------------------------
     def forward(self, z: torch.Tensor):
@@ -61,6 +62,7 @@ class VectorQuantizer(nn.Module):
         z_q, vq_loss, mse, indices, stats = ops.quantize(z, self.embedding.weight,
                                                          float(self.commitment_cost), self.algo)
         self.last_search_stats = stats
+        self.last_mse = mse.detach()  # device copy of the logged loss (multi-GPU statistics need no host round trip)
         if self.return_format == "taming":
             usage, _, _ = ops.codebook_usage(indices, self.num_embeddings)
             p = usage.double() / max(indices.numel(), 1)
