@@ -25,6 +25,8 @@ extern "C" {
  *   "tclow_cluster"      1|2|4  same for the low-D tensor search
  *   "tclow_skip_stages"  0..7   bit mask: 1 tensor kernel, 2 chunk re-score, 4 exact list search (WRONG RESULTS)
  *   "fwd_pass_channels" / "bwd_pass_channels"  64|128|192|256  channels per pass of the tiled tail kernels
+ *   "tail_pipe" / "bwd_pipe"  0|1  pipelined (cp.async double-buffered) 128-token forward tail / backward for
+ *                               D >= 128, D % 64 == 0 (default 1)
  *   "tail_tok128"        0|1    128-token float4 forward-tail kernel for D <= 64 (default 1)
  *   "bwd_warp"           0|1|2  warp-private backward kernel (default 0 = off; measured slower)
  *   "tail_warp"          0|1|2  warp-private forward-tail kernel: off / D >= 128 (default) / any D % 32 == 0
@@ -41,6 +43,9 @@ VQB_API int vqb_fma_peak_launch(int packed, int iters, float* sink, double* flop
  * mode 1 out = a + b, mode 2 linear float4 copy; tensors [B, D, HW] fp32, D % 64 == 0 */
 VQB_API int vqb_ubench_copy(const float* a, const float* b, float* out, int64_t B, int D, int64_t HW, int mode,
                     vqb_stream_t stream);
+/* scatter-reduction pattern of the codebook gradient: every token adds a D-float row of ones into
+ * table[idx[token]] with red.global.add.v4.f32, lanes_per_row (1, 4 or 16) consecutive lanes per row piece */
+VQB_API int vqb_ubench_red(float* table, const int64_t* idx, int64_t N, int D, int lanes_per_row, vqb_stream_t stream);
 /* instruction-mix microbenchmarks of the low-D inner loop (modes in csrc/vqb_ubench.cu);
  * src: >= 10240 floats of finite data */
 VQB_API int vqb_ubench_launch(int mode, int sweeps, const float* src, float* sink, double* flops_host,

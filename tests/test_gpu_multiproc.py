@@ -137,8 +137,14 @@ def _worker(rank, world, port, q):
             moved = float((w_s - base.quantizer.embedding.weight.detach()).abs().max())
             out["ddp_codebook_moved"] = moved > 1e-6
             out["ddp_codebook_equals_global_batch"] = bool(torch.allclose(w_d, w_s, rtol=1e-5, atol=1e-7))
-            worst = max(float((a - b).abs().max()) for a, b in zip(single.parameters(), ddp.module.parameters()))
-            out["ddp_all_params_equal_global_batch"] = worst < 2e-5
+            # Adam's first step moves every weight by ~lr * sign(g): where a gradient is pure rounding noise its sign
+            # (and so 2 * lr) may differ between the two batch splits; everything else must agree closely
+            with torch.no_grad():
+                diffs = torch.cat([(a - b).abs().reshape(-1) for a, b in zip(single.parameters(), ddp.module.parameters())])
+            out["ddp_param_max_diff"] = float(diffs.max())
+            out["ddp_param_frac_above_1e-6"] = float((diffs > 1e-6).float().mean())
+            out["ddp_all_params_equal_global_batch"] = bool(diffs.max() <= 2.05 * 4.5e-5) and \
+                float((diffs > 1e-6).float().mean()) < 1e-3
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -158,5 +164,5 @@ def test_two_rank_modes_match_single_process_results():
         assert p.exitcode == 0
     print("two-rank results:", res[0])
     for r in range(world):
-        bad = [k for k, v in res[r].items() if k != "backend" and v is not True]
+        bad = [k for k, v in res[r].items() if isinstance(v, bool) and v is not True]
         assert not bad, (r, bad, res[r])

@@ -59,6 +59,7 @@ BENCH_PROTOTYPES = {
     "vqb_ubench_launch": (c_int, [c_int, c_int, c_void_p, c_void_p, POINTER(c_double), c_void_p]),
     "vqb_ubench_copy": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p]),
     "vqb_fma_peak_launch": (c_int, [c_int, c_int, c_void_p, POINTER(c_double), c_void_p]),
+    "vqb_ubench_red": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
 }
 
 _lib = None

@@ -119,6 +119,10 @@ extern "C" int vqb_tune(const char* key, int value) {
         set_tail_knob(key, value);
         return VQB_OK;
     }
+    if ((strcmp(key, "tail_pipe") == 0 || strcmp(key, "bwd_pipe") == 0) && value >= 0 && value <= 2) {
+        set_tail_knob(key, value);
+        return VQB_OK;
+    }
     if (strcmp(key, "tail_tok128") == 0 && (value == 0 || value == 1)) {
         set_tail_knob(key, value);
         return VQB_OK;

@@ -480,6 +480,233 @@ __global__ void __launch_bounds__(256, 3)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Pipelined 128-token kernels for large D (D % 64 == 0): the mapping of the tok128 kernel above (512 contiguous
+// bytes of z / g / z_q / dz per warp instruction -- the access pattern that reaches the linear-copy ceiling), with
+// the two things that made it lose at D = 256 removed:
+//   * the codebook rows of the NEXT 64-channel pass are fetched by cp.async (LDGSTS, 16 bytes each, no register
+//     staging) into the other half of a double buffer while the current pass streams, so the L2 latency of the
+//     gathered rows is never exposed behind a barrier;
+//   * the rows are stored token-major [token][64 + 4] exactly as they lie in the codebook -- no transpose on the
+//     way in.  A lane owns 4 consecutive tokens (one float4 along the tokens) and 4 consecutive channels per
+//     step: its 4x4 block of z arrives as four float4 (one per channel), its 4x4 block of e as four LDS.128 (one
+//     per token); the row order in shared memory is permuted (token 4l+j -> row 32j + l) so that the 8 lanes of
+//     a quarter-warp hit 8 distinct 16-byte bank groups (row stride 68 floats = 17 groups).
+// The backward leaves the codebook-gradient terms as one red.global.add.v4.f32 per (token, 4 channels) straight
+// from registers: no second trip through shared memory.
+// ---------------------------------------------------------------------------
+constexpr int kPipeDC = 64;
+constexpr int kPipeStride = kPipeDC + 4;
+constexpr int kPipeBufFloats = kTok128 * kPipeStride;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// codebook rows of the CTA's 128 tokens, channels [d0, d0+64) -> buf[perm(token)][channel]: 2048 16-byte chunks,
+// 8 per thread; 16 consecutive threads copy one 256-byte row segment
+__device__ __forceinline__ void pipe_fill_async(float* buf, const Tile128Tokens& tt, const float* __restrict__ E, int D,
+                                                int d0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int id = threadIdx.x + 256 * i;
+        const int t = id >> 4, q = id & 15;
+        const int r = ((t & 3) << 5) | (t >> 2);
+        cp_async16(buf + r * kPipeStride + 4 * q, E + (size_t)tt.code[t] * D + d0 + 4 * q);
+    }
+}
+
+__device__ __forceinline__ float4 ld_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
+    gather_loss_st_pipe_kernel(const float* __restrict__ z, const float* __restrict__ E, const int64_t* __restrict__ idx,
+                               int64_t N, int D, int64_t HW, int K, float* __restrict__ zq_out,
+                               double* __restrict__ partials, int* __restrict__ err_flag) {
+    extern __shared__ __align__(16) float pipe_smem[];
+    __shared__ Tile128Tokens tt;
+    __shared__ double warp_part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    tile128_load_tokens(tt, idx, N, D, HW, K, err_flag);
+    __syncthreads();
+    const int64_t off = tt.off[lane];
+    const int n_pass = D / kPipeDC;
+    pipe_fill_async(pipe_smem, tt, E, D, 0);
+    cp_async_commit();
+    float sq = 0.f;
+    for (int p = 0; p < n_pass; ++p) {
+        const int d0 = p * kPipeDC;
+        float* buf = pipe_smem + (p & 1) * kPipeBufFloats;
+        if (p + 1 < n_pass) pipe_fill_async(pipe_smem + ((p + 1) & 1) * kPipeBufFloats, tt, E, D, d0 + kPipeDC);
+        cp_async_commit();
+        // this thread's z: 2 chunks of 4 channels x 4 tokens, requested before waiting for the rows
+        float4 zv[2][4];
+        if (off >= 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    zv[h][i] = ld_f4(z + off + (int64_t)(d0 + 4 * (warp + 8 * h) + i) * HW);
+        }
+        cp_async_wait<1>();
+        __syncthreads();  // pass p's rows are visible to every thread
+        if (off >= 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int q = warp + 8 * h;
+                float e[4][4];  // [token j][channel i]
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 v = *reinterpret_cast<const float4*>(buf + (32 * j + lane) * kPipeStride + 4 * q);
+                    e[j][0] = v.x, e[j][1] = v.y, e[j][2] = v.z, e[j][3] = v.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float zz[4] = {zv[h][i].x, zv[h][i].y, zv[h][i].z, zv[h][i].w};
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float diff = __fsub_rn(e[j][i], zz[j]);
+                        o[j] = __fadd_rn(zz[j], diff);
+                        sq = fmaf(diff, diff, sq);
+                    }
+                    *reinterpret_cast<float4*>(zq_out + off + (int64_t)(d0 + 4 * q + i) * HW) =
+                        make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+        __syncthreads();  // done with buf before pass p+2's rows overwrite it
+    }
+    double v = warp_sum_f64((double)sq);
+    if (lane == 0) warp_part[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += warp_part[w];
+        partials[blockIdx.x] = sum;
+    }
+}
+
+// kStage: the codebook-gradient terms go back into the row buffer and leave as half-warp-per-token reductions (256
+// contiguous bytes of one dE row per half-warp) instead of one 16-byte piece of 32 different rows per instruction
+template <int MINB, bool kStage>
+__global__ void __launch_bounds__(256, MINB)
+    backward_pipe_kernel(const float* __restrict__ z, const float* __restrict__ E, const int64_t* __restrict__ idx,
+                         const float* __restrict__ g_zq, const float* __restrict__ g_vq, float beta, float norm, int64_t N,
+                         int D, int64_t HW, int K, float* __restrict__ dz_out, float* __restrict__ dE,
+                         unsigned long long* __restrict__ hist) {
+    extern __shared__ __align__(16) float pipe_smem[];
+    __shared__ Tile128Tokens tt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    tile128_load_tokens(tt, idx, N, D, HW, K, nullptr);
+    __syncthreads();
+    const int64_t off = tt.off[lane];
+    const float gv = g_vq ? __ldg(g_vq) : 0.f;
+    const float gbeta = __fmul_rn(gv, beta);
+    if (hist != nullptr && warp < 4) {
+        const int t = threadIdx.x;  // 0..127
+        const bool live = (int64_t)blockIdx.x * kTok128 + t < N;
+        const unsigned active = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const int k = tt.code[t];
+            const unsigned peers = __match_any_sync(active, k);
+            if (lane == __ffs(peers) - 1) atomicAdd(hist + k, (unsigned long long)__popc(peers));
+        }
+    }
+    int code[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) code[j] = tt.code[4 * lane + j];
+    const int n_pass = D / kPipeDC;
+    pipe_fill_async(pipe_smem, tt, E, D, 0);
+    cp_async_commit();
+    for (int p = 0; p < n_pass; ++p) {
+        const int d0 = p * kPipeDC;
+        float* buf = pipe_smem + (p & 1) * kPipeBufFloats;
+        if (p + 1 < n_pass) pipe_fill_async(pipe_smem + ((p + 1) & 1) * kPipeBufFloats, tt, E, D, d0 + kPipeDC);
+        cp_async_commit();
+        float4 zv[2][4], gz[2][4];
+        if (off >= 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int64_t o = off + (int64_t)(d0 + 4 * (warp + 8 * h) + i) * HW;
+                    zv[h][i] = ld_f4(z + o);
+                    gz[h][i] = g_zq ? ld_f4(g_zq + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+        }
+        cp_async_wait<1>();
+        __syncthreads();
+        if (off >= 0) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int q = warp + 8 * h;
+                float e[4][4];  // [token j][channel i]
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 v = *reinterpret_cast<const float4*>(buf + (32 * j + lane) * kPipeStride + 4 * q);
+                    e[j][0] = v.x, e[j][1] = v.y, e[j][2] = v.z, e[j][3] = v.w;
+                }
+                float ge[4][4];  // codebook-gradient terms [token j][channel i]
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float zz[4] = {zv[h][i].x, zv[h][i].y, zv[h][i].z, zv[h][i].w};
+                    const float gg[4] = {gz[h][i].x, gz[h][i].y, gz[h][i].z, gz[h][i].w};
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float t = __fmul_rn(__fmul_rn(norm, __fsub_rn(zz[j], e[j][i])), gv);
+                        o[j] = __fadd_rn(gg[j], t);
+                        ge[j][i] = __fmul_rn(__fmul_rn(norm, __fsub_rn(e[j][i], zz[j])), gbeta);
+                    }
+                    *reinterpret_cast<float4*>(dz_out + off + (int64_t)(d0 + 4 * q + i) * HW) =
+                        make_float4(o[0], o[1], o[2], o[3]);
+                }
+                if (dE != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if constexpr (kStage)
+                            *reinterpret_cast<float4*>(buf + (32 * j + lane) * kPipeStride + 4 * q) =
+                                make_float4(ge[j][0], ge[j][1], ge[j][2], ge[j][3]);
+                        else
+                            red_add_v4(dE + (size_t)code[j] * D + d0 + 4 * q, ge[j][0], ge[j][1], ge[j][2], ge[j][3]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if constexpr (kStage) {
+            if (dE != nullptr) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int id = threadIdx.x + 256 * i;
+                    const int t = id >> 4, q = id & 15;
+                    if (tt.off[t >> 2] >= 0) {
+                        const int r = ((t & 3) << 5) | (t >> 2);
+                        const float4 v = *reinterpret_cast<const float4*>(buf + r * kPipeStride + 4 * q);
+                        red_add_v4(dE + (size_t)tt.code[t] * D + d0 + 4 * q, v.x, v.y, v.z, v.w);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+static bool pipe_ok(int D, int64_t HW, const void* a, const void* b, const void* c, const void* d) {
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+                           reinterpret_cast<uintptr_t>(d);
+    return D % kPipeDC == 0 && HW % 4 == 0 && (bits & 15u) == 0;
+}
+constexpr size_t kPipeSmemBytes = 2 * sizeof(float) * kPipeBufFloats;  // 69 632 B: three CTAs per SM
+
 static bool tok128_ok(int D, int64_t HW, const void* a, const void* b) {
     return D % 32 == 0 && HW % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u) == 0;
 }
@@ -959,11 +1186,15 @@ VQB_KNOB g_bwd_pass_cap = 64;   // measured best on B200 (profiles/r01_tail_pass
 VQB_KNOB g_fwd_pass_cap = 64;
 VQB_KNOB g_bwd_warp = 0;    // warp-private backward (vqb_tune "bwd_warp")
 VQB_KNOB g_tail_warp = 1;   // warp-private forward tail (vqb_tune "tail_warp": 0 off, 1 auto = D >= 128, 2 force)
+VQB_KNOB g_tail_pipe = 1;   // pipelined 128-token forward tail for D >= 128, D % 64 == 0 (vqb_tune "tail_pipe", 0 = off)
+VQB_KNOB g_bwd_pipe = 1;    // pipelined 128-token backward, same shapes (vqb_tune "bwd_pipe", 0 = off)
 VQB_KNOB g_tail_tok128 = 1;  // 128-token float4 kernels when the layout allows (vqb_tune "tail_tok128", 0 = off)
 #ifdef VQB_EXPERIMENTAL
 namespace vqb {
 void set_tail_knob(const char* key, int value) {
-    if (key[0] == 'b' && key[4] == 'p') g_bwd_pass_cap = value;       // bwd_pass_channels
+    if (key[0] == 't' && key[5] == 'p') g_tail_pipe = value;          // tail_pipe
+    else if (key[0] == 'b' && key[4] == 'p' && key[5] == 'i') g_bwd_pipe = value;  // bwd_pipe
+    else if (key[0] == 'b' && key[4] == 'p') g_bwd_pass_cap = value;  // bwd_pass_channels
     else if (key[0] == 'f') g_fwd_pass_cap = value;                   // fwd_pass_channels
     else if (key[0] == 'b') g_bwd_warp = value;                       // bwd_warp
     else if (key[5] == 'w') g_tail_warp = value;                      // tail_warp
@@ -1011,6 +1242,24 @@ extern "C" int vqb_gather_loss_st_f32(const float* z, const float* E, const int6
             gather_loss_st_tok128_kernel<32><<<(unsigned)tb, 256, 0, s>>>(z, E, idx, N, D, HW, K, zq_out, parts, err_flag);
         VQB_LAUNCH_CHECK("gather_loss_st_tok128_kernel");
         loss_finalize_kernel<<<1, 256, 0, s>>>(parts, tb, 1.0 / ((double)N * D), beta, loss_out);
+        VQB_LAUNCH_CHECK("loss_finalize_kernel");
+        return VQB_OK;
+    }
+    if (g_tail_pipe && D >= 128 && pipe_ok(D, HW, z, zq_out, E, E)) {
+        const int64_t pb = (N + kTok128 - 1) / kTok128;
+        if (g_tail_pipe == 2) {  // 3 CTAs per SM (80 registers, small spill): A/B only, measured slower (0.46 vs 0.38 ms)
+            VQB_CUDA_TRY(cudaFuncSetAttribute(gather_loss_st_pipe_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)kPipeSmemBytes));
+            gather_loss_st_pipe_kernel<3><<<(unsigned)pb, 256, kPipeSmemBytes, s>>>(z, E, idx, N, D, HW, K, zq_out, parts,
+                                                                                   err_flag);
+        } else {
+            VQB_CUDA_TRY(cudaFuncSetAttribute(gather_loss_st_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)kPipeSmemBytes));
+            gather_loss_st_pipe_kernel<2><<<(unsigned)pb, 256, kPipeSmemBytes, s>>>(z, E, idx, N, D, HW, K, zq_out, parts,
+                                                                                   err_flag);
+        }
+        VQB_LAUNCH_CHECK("gather_loss_st_pipe_kernel");
+        loss_finalize_kernel<<<1, 256, 0, s>>>(parts, pb, 1.0 / ((double)N * D), beta, loss_out);
         VQB_LAUNCH_CHECK("loss_finalize_kernel");
         return VQB_OK;
     }
@@ -1083,6 +1332,22 @@ extern "C" int vqb_backward_f32(const float* z, const float* E, const int64_t* i
     const float norm = (float)(2.0 / ((double)N * D));
     unsigned long long* hist = reinterpret_cast<unsigned long long*>(hist_accum);
     const bool v4 = vec4_ok(D, E) && (!dE_accum || (reinterpret_cast<uintptr_t>(dE_accum) & 15u) == 0);
+    if (g_bwd_pipe && D >= 128 && pipe_ok(D, HW, z, dz_out, g_zq, dE_accum)) {
+        const int64_t pb = (N + kTok128 - 1) / kTok128;
+        if (g_bwd_pipe == 2) {  // direct 16-byte reductions from registers (A/B: slower, hot rows serialise)
+            VQB_CUDA_TRY(cudaFuncSetAttribute(backward_pipe_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)kPipeSmemBytes));
+            backward_pipe_kernel<2, false><<<(unsigned)pb, 256, kPipeSmemBytes, s>>>(z, E, idx, g_zq, g_vq, beta, norm, N, D, HW,
+                                                                                    K, dz_out, dE_accum, hist);
+        } else {
+            VQB_CUDA_TRY(cudaFuncSetAttribute(backward_pipe_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)kPipeSmemBytes));
+            backward_pipe_kernel<2, true><<<(unsigned)pb, 256, kPipeSmemBytes, s>>>(z, E, idx, g_zq, g_vq, beta, norm, N, D, HW,
+                                                                                   K, dz_out, dE_accum, hist);
+        }
+        VQB_LAUNCH_CHECK("backward_pipe_kernel");
+        return VQB_OK;
+    }
     if (D % 32 == 0 && ((g_bwd_warp == 1 && D >= 128) || g_bwd_warp == 2)) {
         const int64_t wb = (N + 255) / 256;
         backward_warp_kernel<<<(unsigned)wb, 256, 0, s>>>(z, E, idx, g_zq, g_vq, beta, norm, N, D, HW, K, dz_out, dE_accum,

@@ -221,6 +221,45 @@ extern "C" int vqb_ubench_launch(int mode, int sweeps, const float* src, float* 
     return VQB_OK;
 }
 
+// Scatter-reduction patterns of the codebook gradient: N tokens each add a D-float row into
+// table[idx[token]][0..D).  lanes_per_row consecutive lanes cover lanes_per_row*4 consecutive floats of ONE row per
+// instruction (red.global.add.v4.f32): 1 = lane-per-token (16-byte pieces of 32 different rows per warp instruction),
+// 4 = 64 contiguous bytes per row, 16 = 256 contiguous bytes per row (half-warp per token).  No other memory traffic.
+template <int LPR>
+__global__ void __launch_bounds__(256) red_pattern_kernel(float* __restrict__ table, const int64_t* __restrict__ idx, int64_t N,
+                                                          int D) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    constexpr int TPW = 32 / LPR;                 // tokens per warp instruction
+    const int sub = lane / LPR, l = lane % LPR;   // token slot / position within the row piece
+    // a warp owns 32 consecutive tokens and walks them TPW at a time, each over all D channels
+    for (int t0 = 0; t0 < 32; t0 += TPW) {
+        const int64_t tok = warp_id * 32 + t0 + sub;
+        if (tok >= N) continue;
+        float* row = table + (size_t)idx[tok] * D;
+        for (int c = 4 * l; c < D; c += 4 * LPR)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %1, %1, %1};" ::"l"(row + c), "f"(1.0f) : "memory");
+    }
+}
+
+extern "C" int vqb_ubench_red(float* table, const int64_t* idx, int64_t N, int D, int lanes_per_row, vqb_stream_t stream) {
+    VQB_DEVICE_TRY();
+    if (!table || !idx || N <= 0 || D <= 0 || D % 64 != 0) {
+        set_error("vqb_ubench_red: invalid argument");
+        return VQB_ERR_INVALID_ARG;
+    }
+    const unsigned blocks = (unsigned)((N + 255) / 256);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (lanes_per_row) {
+        case 1: red_pattern_kernel<1><<<blocks, 256, 0, s>>>(table, idx, N, D); break;
+        case 4: red_pattern_kernel<4><<<blocks, 256, 0, s>>>(table, idx, N, D); break;
+        case 16: red_pattern_kernel<16><<<blocks, 256, 0, s>>>(table, idx, N, D); break;
+        default: set_error("vqb_ubench_red: lanes_per_row must be 1, 4 or 16"); return VQB_ERR_INVALID_ARG;
+    }
+    VQB_LAUNCH_CHECK("red_pattern_kernel");
+    return VQB_OK;
+}
+
 // FP32 FMA peak: 16 independent chains per thread, operands from registers
 template <bool kPacked>
 __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float a, float b, float* sink) {
