@@ -387,7 +387,7 @@ def run_conv(args, world, rank, local_rank, device, B, Cin, H, W, Cout, desc, pe
     return line
 
 
-def run_full_step(args, world, rank, local_rank, device, peaks):
+def run_full_step(args, world, rank, local_rank, device, peaks, steps=None, warmup=3):
     """c4 as SURVEY 8(d) specifies it: the reference's own VQVAE (staged in oracle/_ref, default VQGANConfig
     architecture, 67.5 M parameters) with `vqvae.quantizer` swapped for the drop-in (vq_vae.py:82-86), wrapped
     in DistributedDataParallel like accelerate does (train_vqgan.py:197-209), global batch 64 of 256x256 images
@@ -431,8 +431,7 @@ def run_full_step(args, world, rank, local_rank, device, peaks):
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
-    steps = max(3, min(args.steps, 10))
-    warmup = 3
+    steps = steps or max(3, min(args.steps, 10))
     for i in range(warmup):
         step(i)
     barrier()
@@ -855,9 +854,14 @@ def measure_quantizer(args, workload, world, rank, local_rank, device, peaks, fm
                          f"(scalar FFMA {fma_scalar:.1f}, packed FFMA2 {fma_packed:.1f} TFLOP/s); "
                          "MEASURED_PEAKS.json has no FMA figure")
         achieved = flops / (s_ms * 1e-3) / 1e12
+        if algo == 6:
+            peak_note += ("; algo 6 runs the CUDA-core kernel (FP32 FMA pipe) and the tf32x3 tensor kernel side by side on "
+                          f"disjoint images ({int(stats[3])} of {tokens} tokens on the tensor engine): the fraction is the "
+                          "step's algorithmic flops over the FMA-pipe peak alone, i.e. it can exceed what one pipe delivers")
         roofline = {"bound": bound, "kernel": {1: "search_lowd_kernel", 2: "search_fp32_kernel",
                                                3: "search_tc_kernel", 4: "search_tc16_kernel",
-                                               5: "search_tclow_kernel"}.get(algo, str(algo)),
+                                               5: "search_tclow_kernel",
+                                               6: "search_lowd_kernel+search_tclow_kernel"}.get(algo, str(algo)),
                     "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                     "traffic": None, "kernel_ms": s_ms, "algorithmic_flops_per_launch": flops,
                     "algorithmic_bytes_per_launch": tokens * (4 * D + 8) + 4 * K * D,
@@ -888,7 +892,8 @@ def measure_quantizer(args, workload, world, rank, local_rank, device, peaks, fm
             "config": workload_config(workload, world, codebook),
             "details": {"l2": f"{n_rot} rotating input sets ({n_rot * bytes_per_set / 1e6:.0f} MB) > 126 MB L2",
                        "search_algo": {1: "lowd_fma", 2: "fp32_tile", 3: "tcgen05_bf16x3",
-                                       4: "tcgen05_f16_certified", 5: "tcgen05_tf32x3_certified"}.get(algo, str(algo)),
+                                       4: "tcgen05_f16_certified", 5: "tcgen05_tf32x3_certified",
+                                       6: "dual: lowd_fma + tcgen05_tf32x3 side by side"}.get(algo, str(algo)),
                        "cuda_graph": bool(args.graph),
                        "eager_ms_per_step": (eager_ms_total / steps) if eager_ms_total is not None else None,
                        "rescored_tokens_last_step": int(stats[0]),
@@ -1003,9 +1008,18 @@ def run_gpu_arm(args):
     if world > 1:
         B, D, H, W, K, desc = WORKLOADS["c5"]
         c5 = run_sharded_encode(args, world, rank, local_rank, device, B, D, H, W, K, desc, peaks)
+    # configs[3]: the reference's own VQVAE training step with the drop-in inside it (short: 3 timed steps)
+    c4 = None
+    if not args.no_c4:
+        try:
+            c4 = run_full_step(args, world, rank, local_rank, device, peaks, steps=3, warmup=2)
+        except Exception as e:  # the block is context; it must never take the headline down with it
+            c4 = {"workload": "c4full", "failed": f"{type(e).__name__}: {e}"[:300]} if rank == 0 else None
     if rank == 0:
         c3["codebooks"] = variants
         line["c3"] = c3
+        if c4 is not None:
+            line["c4"] = c4
         if c5 is not None:
             line["c5"] = c5
         blocks = [line["parity_check"], c3["parity_check"]] + ([c5["parity_check"]] if c5 else [])
@@ -1028,6 +1042,7 @@ def main():
                     help="codebook law of the quantizer workloads (SURVEY 8d: normal is primary)")
     ap.add_argument("--variants", action="store_true", help="single c2/c3 run: also time the secondary codebooks")
     ap.add_argument("--no-strawman", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="default workload: skip the full VQVAE training-step block")
     ap.add_argument("--algo", type=int, default=0, help="search kernel override (0 = auto)")
     ap.add_argument("--graph", action="store_true",
                     help="time the step as a CUDA-graph replay (vq_gan_b200.graphs); the per-kernel roofline "

@@ -34,6 +34,18 @@ extern "C" {
  *                               4 one MMA in three (WRONG RESULTS) */
 VQB_API int vqb_tune(const char* key, int value);
 
+#define VQB_ALGO_DUAL_LOWD 6 /* experiment: CUDA-core and tf32x3 tensor engines on disjoint images, two streams */
+/* EXPERIMENT (negative result): two-engine variant for D <= 4 and B >= 2 images (config C2: replaces the same quantizer.py:68-76): images
+ * [0, tensor_images) are searched by the tf32x3 tensor pipeline on `aux_stream`, the rest by the CUDA-core kernel on
+ * `stream`, concurrently on the same SMs (they bind different pipes); fork / join by events, so for the caller all
+ * work is ordered on `stream`.  tensor_images < 0 = library default split.  Results are bit-identical to
+ * VQB_ALGO_LOWD_FMA.  stats_out: [0] tokens re-searched exactly, [1] VQB_ALGO_DUAL_LOWD, [3] tokens of the tensor engine. */
+VQB_API size_t vqb_search_dual_workspace_bytes(int64_t B, int D, int64_t HW, int K, int tensor_images);
+VQB_API int vqb_search_dual_f32(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
+                        const void* pack, int64_t* idx_out, float* dmin_out, void* workspace,
+                        size_t workspace_bytes, int tensor_images, int64_t* stats_out,
+                        vqb_stream_t stream, vqb_stream_t aux_stream);
+
 /* FP32 FMA peak microbenchmark (the low-D roofline denominator): launches a register-resident FFMA
  * (packed=0) or FFMA2 (packed=1) loop on every SM and returns the flop count issued; the caller
  * times it with CUDA events. */

@@ -12,9 +12,10 @@ LIB_PATH = os.path.join(_PKG, "lib", "libvqb200.so")
 
 VQB_OK = 0
 ALGO_AUTO, ALGO_LOWD_FMA, ALGO_FP32_TILE, ALGO_TCGEN05, ALGO_TCGEN05_F16, ALGO_TCGEN05_TF32X3 = 0, 1, 2, 3, 4, 5
+ALGO_DUAL_LOWD = 6
 ALGO_NAMES = {ALGO_AUTO: "auto", ALGO_LOWD_FMA: "lowd_fma", ALGO_FP32_TILE: "fp32_tile",
               ALGO_TCGEN05: "tcgen05", ALGO_TCGEN05_F16: "tcgen05_f16",
-              ALGO_TCGEN05_TF32X3: "tcgen05_tf32x3"}
+              ALGO_TCGEN05_TF32X3: "tcgen05_tf32x3", ALGO_DUAL_LOWD: "dual_lowd_fma+tf32x3"}
 
 # name -> (restype, argtypes); must list every symbol include/vqb200.h declares
 PROTOTYPES = {
@@ -60,6 +61,9 @@ BENCH_PROTOTYPES = {
     "vqb_ubench_copy": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p]),
     "vqb_fma_peak_launch": (c_int, [c_int, c_int, c_void_p, POINTER(c_double), c_void_p]),
     "vqb_ubench_red": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "vqb_search_dual_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64, c_int, c_int]),
+    "vqb_search_dual_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -171,8 +171,9 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 
 // launch entry points implemented in the per-kernel translation units
 int launch_codebook_prepare(const float* E, int K, int D, void* pack, cudaStream_t s);
+// ctas_per_sm: 0 = the kernel's own residency (2 CTAs per SM); 1 leaves half of every SM to a co-running kernel
 int launch_search_lowd(const float* z, int64_t B, int D, int64_t HW, int K, const void* pack,
-                       int64_t* idx_out, float* dmin_out, cudaStream_t s);
+                       int64_t* idx_out, float* dmin_out, cudaStream_t s, int ctas_per_sm = 0);
 size_t search_fp32_workspace_bytes(int64_t n_rows, int D = 0);
 int launch_search_fp32(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                        const void* pack, const int32_t* token_list, const int32_t* list_count,
@@ -185,7 +186,7 @@ int launch_search_tc(const float* z, int64_t B, int D, int64_t HW, const float* 
 size_t search_tclow_workspace_bytes(int64_t n_tokens, int D, int K);
 int launch_search_tclow(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                         const void* pack, int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes,
-                        int64_t* stats_out, cudaStream_t s);
+                        int64_t* stats_out, cudaStream_t s, bool share_sm = false);
 int launch_search_lowd_list(const float* z, int64_t B, int D, int64_t HW, int K, const void* pack,
                             const int32_t* list, const int32_t* list_count, int64_t* idx_out,
                             float* dmin_out, cudaStream_t s);

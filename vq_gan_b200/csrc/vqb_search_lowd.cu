@@ -353,26 +353,34 @@ __global__ void __launch_bounds__(LowDCfg<D, V>::kThreads, LowDCfg<D, V>::kMinBl
 template <int D, int V>
 static int launch_lowd_t(const float* z, int64_t N, int64_t HW, int K, const void* pack,
                          int64_t* idx_out, float* dmin_out, cudaStream_t s, const int32_t* list = nullptr,
-                         const int32_t* list_count = nullptr) {
+                         const int32_t* list_count = nullptr, int ctas_per_sm = 0) {
     using Cfg = LowDCfg<D, V>;
     constexpr int kLowDThreads = Cfg::kThreads;
     auto kernel = list ? search_lowd_kernel<D, V, true> : search_lowd_kernel<D, V, false>;
-    VQB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes));
+    // the largest shared-memory carve-out, whatever this kernel needs by itself: an SM only runs kernels that agree on
+    // the L1 / shared split, and the two-engine search (vqb_search_dual_f32) co-schedules this kernel with the tensor
+    // kernel (measured: with the default carve-outs the second kernel waits for the first to drain)
+    VQB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     const PackLayout L = pack_layout(K, D);
     // persistent: one wave of resident CTAs
-    const int slots = sm_count() * ((g_lowd_ctas_per_sm > 0 && g_lowd_ctas_per_sm < Cfg::kMinBlocks) ? g_lowd_ctas_per_sm
-                                                                                                      : Cfg::kMinBlocks);
+    if (ctas_per_sm <= 0) ctas_per_sm = g_lowd_ctas_per_sm;
+    // one CTA per SM on purpose (two-engine search): ask for more than half of the SM's shared memory so that the
+    // hardware cannot stack two of these CTAs on one SM and leave others empty -- the co-running tensor kernel needs
+    // a slot on EVERY SM (113 + 111 KB + bookkeeping = the whole 228 KB)
+    const size_t smem_bytes = ctas_per_sm == 1 && Cfg::kSmemBytes < (size_t)113 * 1024 ? (size_t)113 * 1024 : Cfg::kSmemBytes;
+    VQB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    const int slots = sm_count() * ((ctas_per_sm > 0 && ctas_per_sm < Cfg::kMinBlocks) ? ctas_per_sm : Cfg::kMinBlocks);
     int64_t per_cta = (N + slots - 1) / slots;
     per_cta = (per_cta + kLowDThreads - 1) / kLowDThreads * kLowDThreads;
     const int grid = list ? slots : (int)((N + per_cta - 1) / per_cta);
-    kernel<<<grid, kLowDThreads, Cfg::kSmemBytes, s>>>(
+    kernel<<<grid, kLowDThreads, smem_bytes, s>>>(
         z, N, HW, K, static_cast<const unsigned char*>(pack), L, per_cta, list, list_count, idx_out, dmin_out);
     VQB_LAUNCH_CHECK("search_lowd_kernel");
     return VQB_OK;
 }
 
 int launch_search_lowd(const float* z, int64_t B, int D, int64_t HW, int K, const void* pack,
-                       int64_t* idx_out, float* dmin_out, cudaStream_t s) {
+                       int64_t* idx_out, float* dmin_out, cudaStream_t s, int ctas_per_sm) {
     const int64_t N = B * HW;
     if (D == 4 && g_lowd_variant != 0) {  // tuning variants are only instantiated for the headline D
         switch (g_lowd_variant) {
@@ -386,7 +394,7 @@ int launch_search_lowd(const float* z, int64_t B, int D, int64_t HW, int K, cons
     switch (D) {
 #define VQB_CASE(d) \
     case d:         \
-        return launch_lowd_t<d, 0>(z, N, HW, K, pack, idx_out, dmin_out, s);
+        return launch_lowd_t<d, 0>(z, N, HW, K, pack, idx_out, dmin_out, s, nullptr, nullptr, ctas_per_sm);
         VQB_CASE(1) VQB_CASE(2) VQB_CASE(3) VQB_CASE(4) VQB_CASE(5) VQB_CASE(6) VQB_CASE(7) VQB_CASE(8)
         VQB_CASE(9) VQB_CASE(10) VQB_CASE(11) VQB_CASE(12) VQB_CASE(13) VQB_CASE(14) VQB_CASE(15)
         VQB_CASE(16)

@@ -127,6 +127,7 @@ struct LowParams {
     int32_t* chunk;            // [N] winning 32-code chunk
     int32_t* list;             // tokens that need the exact full search
     int32_t* list_count;
+    int share_sm;              // host only: launched next to the CUDA-core kernel (two-engine search)
 };
 
 template <int CL>
@@ -473,8 +474,13 @@ static int launch_tclow_cl(const LowParams& p0, cudaStream_t s) {
     p.n_stages = stages;
     size_t smem = 1024 + (2 + (size_t)stages) * tile_bytes + 512 + 2 * kLowRows * 4 * sizeof(float);
     // every CTA allocates all 512 TMEM columns: never let two of them share an SM
-    if (smem < 116 * 1024) smem = 116 * 1024;
+    // (111 KB when it shares the SM with the CUDA-core kernel of the two-engine search, which takes 113 KB)
+    const size_t floor_bytes = (size_t)(p.share_sm ? 111 : 116) * 1024;
+    if (smem < floor_bytes) smem = floor_bytes;
     VQB_CUDA_TRY(cudaFuncSetAttribute(search_tclow_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // same L1 / shared split as search_lowd_kernel so that both can be resident on one SM (vqb_search_dual_f32)
+    VQB_CUDA_TRY(cudaFuncSetAttribute(search_tclow_kernel<CL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
     VQB_CUDA_TRY(cudaFuncSetAttribute(search_tclow_kernel<CL>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       (int)cudaSharedmemCarveoutMaxShared));
     const int n_m_tiles = (int)((p.N + kLowRows - 1) / kLowRows);
@@ -508,7 +514,7 @@ static int launch_tclow_cl(const LowParams& p0, cudaStream_t s) {
 template <int D>
 static int launch_tclow_d(const float* z, int64_t N, int64_t HW, const float* E, int K, const unsigned char* pk,
                           const PackLayout& L, unsigned char* wsb, const LowWorkspace& w, int64_t* idx_out,
-                          float* dmin_out, cudaStream_t s) {
+                          float* dmin_out, cudaStream_t s, bool share_sm) {
     float* img = reinterpret_cast<float*>(wsb + w.off_img);
     float4* tok_norms = reinterpret_cast<float4*>(wsb + w.off_tau);
     int32_t* chunk = reinterpret_cast<int32_t*>(wsb + w.off_chunk);
@@ -532,6 +538,7 @@ static int launch_tclow_d(const float* z, int64_t N, int64_t HW, const float* E,
     p.chunk = chunk;
     p.list = list;
     p.list_count = count;
+    p.share_sm = share_sm ? 1 : 0;
     int rc = VQB_OK;
     if (g_tclow_debug & 1) {
         VQB_CUDA_TRY(cudaMemsetAsync(chunk, 0, sizeof(int32_t) * (size_t)N, s));
@@ -553,7 +560,7 @@ static int launch_tclow_d(const float* z, int64_t N, int64_t HW, const float* E,
 
 int launch_search_tclow(const float* z, int64_t B, int D, int64_t HW, const float* E, int K, const void* pack,
                         int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes, int64_t* stats_out,
-                        cudaStream_t s) {
+                        cudaStream_t s, bool share_sm) {
     const int64_t N = B * HW;
     const LowWorkspace w = low_workspace(N, D);
     if (!ws || ws_bytes < w.total) {
@@ -571,7 +578,7 @@ int launch_search_tclow(const float* z, int64_t B, int D, int64_t HW, const floa
     switch (D) {
 #define VQB_CASE(d)                                                                            \
     case d:                                                                                    \
-        rc = launch_tclow_d<d>(z, N, HW, E, K, pk, L, wsb, w, idx_out, dmin_out, s);           \
+        rc = launch_tclow_d<d>(z, N, HW, E, K, pk, L, wsb, w, idx_out, dmin_out, s, share_sm); \
         break;
         VQB_CASE(1) VQB_CASE(2) VQB_CASE(3) VQB_CASE(4) VQB_CASE(5) VQB_CASE(6) VQB_CASE(7) VQB_CASE(8)
         VQB_CASE(9) VQB_CASE(10) VQB_CASE(11) VQB_CASE(12) VQB_CASE(13) VQB_CASE(14) VQB_CASE(15)
