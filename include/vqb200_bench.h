@@ -21,6 +21,7 @@ extern "C" {
 
 /*   "lowd_variant"       0..4   launch shape of the CUDA-core low-D search (0 = 256 threads x 2 CTA/SM)
  *   "lowd_ctas_per_sm"   0..3   0 = the variant's own residency; 1 leaves room for a co-running kernel
+ *   "dual_permille"      1..999 share of the images handed to the tensor role of the two-engine search (algo 6)
  *   "tc16_cluster"       1|2|4  cluster size (codebook-stage multicast) of the fp16 tensor search
  *   "tclow_cluster"      1|2|4  same for the low-D tensor search
  *   "tclow_skip_stages"  0..7   bit mask: 1 tensor kernel, 2 chunk re-score, 4 exact list search (WRONG RESULTS)
@@ -33,18 +34,6 @@ extern "C" {
  *   "conv_debug"         0..15  bit mask for the 1x1 convolution: 1 no activation loads, 2 no stores,
  *                               4 one MMA in three (WRONG RESULTS) */
 VQB_API int vqb_tune(const char* key, int value);
-
-#define VQB_ALGO_DUAL_LOWD 6 /* experiment: CUDA-core and tf32x3 tensor engines on disjoint images, two streams */
-/* EXPERIMENT (negative result): two-engine variant for D <= 4 and B >= 2 images (config C2: replaces the same quantizer.py:68-76): images
- * [0, tensor_images) are searched by the tf32x3 tensor pipeline on `aux_stream`, the rest by the CUDA-core kernel on
- * `stream`, concurrently on the same SMs (they bind different pipes); fork / join by events, so for the caller all
- * work is ordered on `stream`.  tensor_images < 0 = library default split.  Results are bit-identical to
- * VQB_ALGO_LOWD_FMA.  stats_out: [0] tokens re-searched exactly, [1] VQB_ALGO_DUAL_LOWD, [3] tokens of the tensor engine. */
-VQB_API size_t vqb_search_dual_workspace_bytes(int64_t B, int D, int64_t HW, int K, int tensor_images);
-VQB_API int vqb_search_dual_f32(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
-                        const void* pack, int64_t* idx_out, float* dmin_out, void* workspace,
-                        size_t workspace_bytes, int tensor_images, int64_t* stats_out,
-                        vqb_stream_t stream, vqb_stream_t aux_stream);
 
 /* FP32 FMA peak microbenchmark (the low-D roofline denominator): launches a register-resident FFMA
  * (packed=0) or FFMA2 (packed=1) loop on every SM and returns the flop count issued; the caller

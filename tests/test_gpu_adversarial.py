@@ -40,6 +40,11 @@ def test_lowd_tensor_path_equals_fma_kernel_on_adversarial_data(kind, D, K):
     i5, d5, st = ops.search(z.cuda(), E.cuda(), 5)
     print(f"{kind} D={D} K={K}: {int(st[0])} of {i1.numel()} tokens re-searched exactly")
     assert torch.equal(i1, i5) and torch.equal(d1, d5)
+    if D == 4:  # the two-engine kernel splits by images: view the same tokens as a batch of 8 "images"
+        zb = z.view(D, 8, -1).permute(1, 0, 2).contiguous().cuda()          # [8, D, N/8]
+        j1, e1, _ = ops.search(zb, E.cuda(), 1)
+        j6, e6, st6 = ops.search(zb, E.cuda(), 6)
+        assert int(st6[1]) == 6 and torch.equal(j1, j6) and torch.equal(e1, e6)
 
 
 @pytest.mark.parametrize("kind", ["grid", "clustered", "scaled", "tiny_codes", "outliers"])

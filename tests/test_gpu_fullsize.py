@@ -73,6 +73,11 @@ def test_c2_tensor_path_is_bit_identical_to_fma_kernel():
         print(f"c2 {name}: unsure tokens re-searched exactly = {int(st[0])} of {i1.numel()}")
         assert int(st[1]) == 5
         assert torch.equal(i1, i5) and torch.equal(d1, d5)
+        # both engines in one CTA (the default for this shape): same bits again
+        i6, d6, st6 = ops.search(zc, Ec, 6)
+        i0, d0, st0 = ops.search(zc, Ec, 0)
+        assert int(st6[1]) == 6 and int(st0[1]) == 6 and 0 < int(st6[3]) < i1.numel()
+        assert torch.equal(i1, i6) and torch.equal(d1, d6) and torch.equal(i1, i0)
     # other low dimensions (different numbers of k-steps), ragged token count, K not a multiple of 128
     for D, Kx, B, HW in ((1, 700, 3, 331), (3, 1000, 5, 1024), (8, 5000, 9, 777), (16, 4099, 7, 1024)):
         g = torch.Generator().manual_seed(D)

@@ -61,9 +61,6 @@ BENCH_PROTOTYPES = {
     "vqb_ubench_copy": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p]),
     "vqb_fma_peak_launch": (c_int, [c_int, c_int, c_void_p, POINTER(c_double), c_void_p]),
     "vqb_ubench_red": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
-    "vqb_search_dual_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64, c_int, c_int]),
-    "vqb_search_dual_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                    c_void_p, c_size_t, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -99,6 +99,10 @@ extern "C" int vqb_tune(const char* key, int value) {
         set_lowd_variant(16 + value);
         return VQB_OK;
     }
+    if (strcmp(key, "dual_permille") == 0 && value >= 1 && value <= 999) {
+        set_dual_permille(value);
+        return VQB_OK;
+    }
     if (strcmp(key, "tc16_cluster") == 0 && (value == 1 || value == 2 || value == 4)) {
         set_tc16_cluster(value);
         return VQB_OK;
@@ -164,10 +168,13 @@ extern "C" int vqb_codebook_prepare_f32(const float* E, int K, int D, void* pack
 // Measured on B200 (profiles/r01_tclow_vs_fma.txt): the CUDA-core kernel costs ~0.72 ms per 1M tokens x
 // 16384 codes x dimension; the tf32x3 tensor kernel is bound by TMEM traffic at ~2.5-5 ms per 1M x 16384
 // for any D <= 16, with a higher fixed cost.  So: FMA for D <= 4 and for small problems, tensor above.
-static int resolve_algo(int algo, int D, int64_t N = 0, int K = 0) {
+static int resolve_algo(int algo, int D, int64_t N = 0, int K = 0, int64_t B = 0) {
     if (algo != VQB_ALGO_AUTO) return algo;
     if (D <= kLowDMax) {
         const bool large = (double)N * (double)K >= 268435456.0;  // 2^28 scores
+        // D = 4 (config C2) with enough images to split: both engines in one CTA, 2.32 ms against 2.94 (CUDA cores)
+        // and 2.82 (tensor cores) per 1M tokens x 16384 codes, identical results
+        if (dual_eligible(B, D) && B >= 16 && (double)N * (double)K >= 1073741824.0) return VQB_ALGO_DUAL_LOWD;
         return (D >= 5 && large) ? VQB_ALGO_TCGEN05_TF32X3 : VQB_ALGO_LOWD_FMA;
     }
     if (tc16_eligible_dim(D)) {
@@ -181,10 +188,11 @@ static int resolve_algo(int algo, int D, int64_t N = 0, int K = 0) {
 
 extern "C" size_t vqb_search_workspace_bytes(int64_t B, int D, int64_t HW, int K, int algo) {
     if (B < 0 || HW < 0 || D <= 0 || K <= 0) return 0;
-    const int a = resolve_algo(algo, D, B * HW, K);
+    const int a = resolve_algo(algo, D, B * HW, K, B);
     if (a == VQB_ALGO_TCGEN05) return search_tc_workspace_bytes(B * HW, D, K);
     if (a == VQB_ALGO_TCGEN05_F16) return search_tc16_workspace_bytes(B * HW, D, K);
     if (a == VQB_ALGO_TCGEN05_TF32X3) return search_tclow_workspace_bytes(B * HW, D, K);
+    if (a == VQB_ALGO_DUAL_LOWD) return search_dual_workspace_bytes(B, D, HW, K);
     if (a == VQB_ALGO_FP32_TILE) return search_fp32_workspace_bytes(B * HW);
     return 0;
 }
@@ -215,7 +223,7 @@ extern "C" int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, cons
         return VQB_ERR_INVALID_ARG;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int a = resolve_algo(algo, D, N, K);
+    const int a = resolve_algo(algo, D, N, K, B);
     int rc;
     switch (a) {
         case VQB_ALGO_LOWD_FMA:
@@ -251,6 +259,12 @@ extern "C" int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, cons
             }
             return launch_search_tclow(z, B, D, HW, E, K, pack, idx_out, dmin_out, workspace, workspace_bytes,
                                        stats_out, s);
+        case VQB_ALGO_DUAL_LOWD:
+            if (!dual_eligible(B, D)) {
+                set_error("VQB_ALGO_DUAL_LOWD needs D == %d and at least 2 images, got D=%d B=%lld", kDualD, D, (long long)B);
+                return VQB_ERR_UNSUPPORTED;
+            }
+            return launch_search_dual(z, B, D, HW, E, K, pack, idx_out, dmin_out, workspace, workspace_bytes, stats_out, s);
         default:
             set_error("vqb_search_f32: unknown algo %d", algo);
             return VQB_ERR_INVALID_ARG;
@@ -262,114 +276,3 @@ extern "C" int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, cons
     }
     return VQB_OK;
 }
-
-#ifdef VQB_EXPERIMENTAL
-// ---------------------------------------------------------------------------
-// Two-engine search for D <= 4 (config C2).  The CUDA-core kernel (FP32 FMA pipe; bound by the one ALU-pipe
-// minimum per score) and the tf32x3 tensor kernel (bound by TMEM read-back) saturate DIFFERENT resources of the SM
-// and both fit on it at once (128 x 256 + 80 x 352 registers, 82 + 116 KB shared memory).  The batch is split by
-// images: the first `tensor_images` go through the tensor pipeline on `aux_stream`, the rest through the CUDA-core
-// kernel at one CTA per SM on `stream`; fork / join by events, so the call is still "enqueue on `stream`" for the
-// caller (and capturable into a CUDA graph).  Both engines return bit-identical results, so
-// the split is invisible in the output.
-//
-// MEASUREMENT BUILD ONLY (libvqb200_bench.so): on B200 the two kernels do NOT become co-resident -- with either
-// launch order, the same shared-memory carve-out on both and shared-memory requests padded so that exactly one CTA of
-// each fits an SM, the second kernel starts when the first one drains (scripts/dual_ab.py, scripts/hybrid_probe.py:
-// 2.86-3.05 ms against 2.94 ms for the CUDA-core kernel alone at C2).  Kept as the harness for that experiment.
-// ---------------------------------------------------------------------------
-static int64_t dual_tensor_images(int64_t B, int D, int tensor_images) {
-    if (tensor_images >= 0) return tensor_images > B ? B : tensor_images;
-    // time per token: CUDA cores ~ D (0.72 ms per 1M x 16384 x dim, +~20 % at one CTA per SM), tensor ~ constant 2.6 ms
-    const double t_fma = 0.72 * D * 1.2, t_tc = 2.6;
-    int64_t bt = (int64_t)((double)B * t_fma / (t_fma + t_tc) + 0.5);
-    return bt < 1 ? 1 : (bt > B - 1 ? B - 1 : bt);
-}
-
-extern "C" size_t vqb_search_dual_workspace_bytes(int64_t B, int D, int64_t HW, int K, int tensor_images) {
-    if (B < 2 || HW <= 0 || D <= 0 || D > 4 || K <= 0) return 0;
-    return search_tclow_workspace_bytes(dual_tensor_images(B, D, tensor_images) * HW, D, K) + 256;
-}
-
-__global__ void dual_stats_kernel(int64_t* stats, const int64_t* tensor_stats, int64_t tensor_tokens) {
-    stats[0] = tensor_stats[0];
-    stats[1] = VQB_ALGO_DUAL_LOWD;
-    stats[2] = 0;
-    stats[3] = tensor_tokens;
-}
-
-extern "C" int vqb_search_dual_f32(const float* z, int64_t B, int D, int64_t HW, const float* E, int K, const void* pack,
-                                   int64_t* idx_out, float* dmin_out, void* workspace, size_t workspace_bytes,
-                                   int tensor_images, int64_t* stats_out, vqb_stream_t stream, vqb_stream_t aux_stream) {
-    VQB_DEVICE_TRY();
-    if (B < 2 || HW <= 0 || D <= 0 || D > 4 || K <= 0 || !z || !E || !pack || !idx_out || !workspace) {
-        set_error("vqb_search_dual_f32: needs B >= 2 images, 1 <= D <= 4 and non-null buffers (B=%lld D=%d)", (long long)B, D);
-        return VQB_ERR_INVALID_ARG;
-    }
-    if (B * HW >= (1LL << 31)) {
-        set_error("vqb_search_dual_f32: at most 2^31-1 tokens per call");
-        return VQB_ERR_INVALID_ARG;
-    }
-    if (stream == aux_stream) {
-        set_error("vqb_search_dual_f32: aux_stream must differ from stream");
-        return VQB_ERR_INVALID_ARG;
-    }
-    const int64_t Bt = dual_tensor_images(B, D, tensor_images);
-    if (Bt <= 0 || Bt >= B) {
-        set_error("vqb_search_dual_f32: tensor_images must leave both engines at least one image (got %lld of %lld)",
-                  (long long)Bt, (long long)B);
-        return VQB_ERR_INVALID_ARG;
-    }
-    const size_t need = search_tclow_workspace_bytes(Bt * HW, D, K) + 256;
-    if (workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) {
-        set_error("vqb_search_dual_f32: workspace too small or not 256-byte aligned (%zu < %zu)", workspace_bytes, need);
-        return VQB_ERR_WORKSPACE;
-    }
-    cudaStream_t s = static_cast<cudaStream_t>(stream), aux = static_cast<cudaStream_t>(aux_stream);
-    cudaEvent_t fork = nullptr, join = nullptr;
-    VQB_CUDA_TRY(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-    cudaError_t e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
-    if (e != cudaSuccess) {
-        cudaEventDestroy(fork);
-        return cuda_fail(e, "cudaEventCreateWithFlags");
-    }
-    int rc = VQB_OK;
-    int64_t* tstats = reinterpret_cast<int64_t*>(workspace);  // first 256 bytes: the tensor engine's statistics
-    unsigned char* ws = static_cast<unsigned char*>(workspace) + 256;
-    do {
-        if ((e = cudaEventRecord(fork, s)) != cudaSuccess || (e = cudaStreamWaitEvent(aux, fork, 0)) != cudaSuccess) {
-            rc = cuda_fail(e, "fork");
-            break;
-        }
-        const int64_t off_tok = Bt * HW;
-#ifdef VQB_EXPERIMENTAL
-        const bool tensor_first = getenv("VQB_DUAL_TENSOR_FIRST") != nullptr;
-#else
-        constexpr bool tensor_first = false;
-#endif
-        // CUDA-core engine first: its 148 CTAs take one slot of every SM, the tensor CTAs then fill the other
-        if (tensor_first) {
-            rc = launch_search_tclow(z, Bt, D, HW, E, K, pack, idx_out, dmin_out, ws, workspace_bytes - 256, tstats, aux, true);
-            if (rc != VQB_OK) break;
-        }
-        rc = launch_search_lowd(z + off_tok * D, B - Bt, D, HW, K, pack, idx_out + off_tok,
-                                dmin_out ? dmin_out + off_tok : nullptr, s, 1);
-        if (rc != VQB_OK) break;
-        if (!tensor_first) {
-            rc = launch_search_tclow(z, Bt, D, HW, E, K, pack, idx_out, dmin_out, ws, workspace_bytes - 256, tstats, aux, true);
-            if (rc != VQB_OK) break;
-        }
-        if ((e = cudaEventRecord(join, aux)) != cudaSuccess || (e = cudaStreamWaitEvent(s, join, 0)) != cudaSuccess) {
-            rc = cuda_fail(e, "join");
-            break;
-        }
-        if (stats_out) {
-            dual_stats_kernel<<<1, 1, 0, s>>>(stats_out, tstats, Bt * HW);
-            if ((e = cudaGetLastError()) != cudaSuccess) rc = cuda_fail(e, "dual_stats_kernel");
-        }
-    } while (0);
-    cudaEventDestroy(fork);  // released once the enqueued work that uses them has completed
-    cudaEventDestroy(join);
-    return rc;
-}
-#endif  // VQB_EXPERIMENTAL

@@ -187,11 +187,18 @@ size_t search_tclow_workspace_bytes(int64_t n_tokens, int D, int K);
 int launch_search_tclow(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                         const void* pack, int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes,
                         int64_t* stats_out, cudaStream_t s, bool share_sm = false);
+// two engines in one CTA (D = 4): CUDA-core role + tensor role on disjoint images (vqb_search_tclow.cu)
+constexpr int kDualD = 4;
+__host__ __device__ inline bool dual_eligible(int64_t B, int D) { return D == kDualD && B >= 2; }
+size_t search_dual_workspace_bytes(int64_t B, int D, int64_t HW, int K);
+int launch_search_dual(const float* z, int64_t B, int D, int64_t HW, const float* E, int K, const void* pack,
+                       int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes, int64_t* stats_out, cudaStream_t s);
 int launch_search_lowd_list(const float* z, int64_t B, int D, int64_t HW, int K, const void* pack,
                             const int32_t* list, const int32_t* list_count, int64_t* idx_out,
                             float* dmin_out, cudaStream_t s);
 #ifdef VQB_EXPERIMENTAL
 void set_tclow_cluster(int c);
+void set_dual_permille(int v);
 void set_tail_knob(const char* key, int value);
 void set_conv_debug(int v);
 #endif

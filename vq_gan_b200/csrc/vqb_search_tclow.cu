@@ -22,6 +22,7 @@
 // Pipeline: persistent CTA per SM, 128-token tiles (A double buffered), 128-code B stages streamed
 // with 1-D bulk copies of pre-built shared-memory images (SWIZZLE_NONE K-major; cluster multicast:
 // every CTA of a cluster fetches 1/CL of each stage), four 128-column TMEM accumulators.
+#include "vqb_lowd_body.cuh"
 #include "vqb_tc_common.cuh"
 
 namespace vqb {
@@ -130,9 +131,20 @@ struct LowParams {
     int share_sm;              // host only: launched next to the CUDA-core kernel (two-engine search)
 };
 
-template <int CL>
-__global__ void __launch_bounds__(kLowThreads, 2) search_tclow_kernel(LowParams p) {  // <= 85 registers: can share an SM with the CUDA-core kernel
-    extern __shared__ unsigned char smem_unaligned[];
+// barrier over the 384 threads of the tensor role: the whole CTA (BAR = 0) or a named barrier (search_dual_kernel)
+template <int BAR>
+__device__ __forceinline__ void tclow_sync() {
+    if constexpr (BAR == 0)
+        __syncthreads();
+    else
+        asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(kLowThreads) : "memory");
+}
+
+// The CTA program of the tensor search (384 threads: TID0 .. TID0 + 383): the body of search_tclow_kernel and the
+// tensor role of search_dual_kernel.  The cluster barriers inside are executed by EVERY thread of the cluster's CTAs
+// (search_dual_kernel makes its FMA role arrive at the same two points).
+template <int CL, int TID0, int BAR>
+__device__ __forceinline__ void tclow_cta_body(const LowParams& p, unsigned char* smem_unaligned, int cta_index, int n_ctas) {  // <= 85 registers: can share an SM with the CUDA-core kernel
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) &
                                                            ~(uintptr_t)1023);
     const uint32_t tile_bytes = (uint32_t)p.steps * (kLowRows * 32);  // A tile and B stage have the same shape
@@ -148,15 +160,16 @@ __global__ void __launch_bounds__(kLowThreads, 2) search_tclow_kernel(LowParams 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12 + 2 * kLowMaxStages);
     float* xchg = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 512);  // [2][128][4]
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = (int)threadIdx.x - TID0;  // thread index within the tensor role
+    const int warp = tid >> 5, lane = tid & 31;
     const int n_m_tiles = (int)((p.N + kLowRows - 1) / kLowRows);
     const int n_n_tiles = p.Kpad / kLowBN;  // even: Kpad is a multiple of 256
-    const int n_rounds = (n_m_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_rounds = (n_m_tiles + n_ctas - 1) / n_ctas;
     const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
     constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1);
     const int n_stages = p.n_stages;
 
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             tc_mbar_init(a_full + i, 1);
             tc_mbar_init(a_empty + i, 1);
@@ -177,7 +190,7 @@ __global__ void __launch_bounds__(kLowThreads, 2) search_tclow_kernel(LowParams 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    tclow_sync<BAR>();
     if constexpr (CL > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
@@ -187,7 +200,7 @@ __global__ void __launch_bounds__(kLowThreads, 2) search_tclow_kernel(LowParams 
         if (lane == 0) {
             uint32_t stage = 0, bphase = 0;
             for (int round = 0; round < n_rounds; ++round) {
-                int mt = blockIdx.x + round * gridDim.x;
+                int mt = cta_index + round * n_ctas;
                 if (mt >= n_m_tiles) mt = n_m_tiles - 1;  // padding round of a cluster: rows are dropped later
                 const int ab = round & 1;
                 tc_mbar_wait(a_empty + ab, ((round >> 1) & 1) ^ 1);
@@ -254,7 +267,7 @@ __global__ void __launch_bounds__(kLowThreads, 2) search_tclow_kernel(LowParams 
         const float rho_r = __int_as_float(p.header[12]), rho_l = __int_as_float(p.header[14]);
         const int row_in_tile = q * 32 + lane;
         for (int round = 0; round < n_rounds; ++round) {
-            const int mt = blockIdx.x + round * gridDim.x;
+            const int mt = cta_index + round * n_ctas;
             const int64_t row = (int64_t)mt * kLowRows + row_in_tile;
             float m1 = INFINITY, m2 = INFINITY;
             int id = 0;
@@ -341,11 +354,56 @@ __global__ void __launch_bounds__(kLowThreads, 2) search_tclow_kernel(LowParams 
     }
 
     tc_fence_before();
-    __syncthreads();
+    tclow_sync<BAR>();
     if constexpr (CL > 1) cluster_sync_all();
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+template <int CL>
+__global__ void __launch_bounds__(kLowThreads, 2) search_tclow_kernel(LowParams p) {  // <= 85 registers
+    extern __shared__ unsigned char smem_unaligned[];
+    tclow_cta_body<CL, 0, 0>(p, smem_unaligned, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// ---------------------------------------------------------------------------
+// Two engines in ONE CTA (D = 4, config C2): warps 0-7 run the CUDA-core search (FP32 FMA pipe; bound by the one
+// ALU-pipe minimum per score), warps 8-19 the tensor search (tcgen05 tf32x3; bound by TMEM read-back).  They bind
+// different resources of the SM, work on disjoint token ranges, and return bit-identical results, so the split is
+// invisible in the output.  (Launching the two kernels side by side on two streams does NOT work on B200: the second
+// kernel only starts when the first drains -- DESIGN.md section 4.2 -- hence one kernel, where co-residency is by
+// construction.)  Registers: the CTA starts at 96 per thread; the tensor warpgroups drop to 80 and the FMA warpgroups
+// take 120 with setmaxnreg (the pool is what the CTA itself released: 384 x 16 = 256 x 24).
+// ---------------------------------------------------------------------------
+constexpr int kDualFmaThreads = 256;
+constexpr int kDualThreads = kDualFmaThreads + kLowThreads;  // 640
+
+struct DualFmaParams {
+    const float* z;        // first image of the FMA range
+    int64_t N, HW;
+    int K;
+    const unsigned char* pack;
+    PackLayout L;
+    int64_t tokens_per_cta;
+    int64_t* idx_out;      // of the FMA range
+    float* dmin_out;       // nullable
+    uint32_t tensor_smem_offset;  // dynamic shared memory: [FMA tiles | tensor role]
+};
+
+template <int D, int CL>
+__global__ void __launch_bounds__(kDualThreads, 1) search_dual_kernel(LowParams pt, DualFmaParams pf) {
+    extern __shared__ __align__(1024) unsigned char dual_smem[];
+    if (threadIdx.x < kDualFmaThreads) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");  // 256 x (120 - 96) = 6144 = what the tensor warps release
+        if constexpr (CL > 1) cluster_sync_all();  // matches the tensor role's barrier after its mbarrier init
+        lowd_cta_body<D, 0, false, 2>(pf.z, pf.N, pf.HW, pf.K, pf.pack, pf.L, pf.tokens_per_cta, nullptr, nullptr, pf.idx_out,
+                                      pf.dmin_out, dual_smem, (int)blockIdx.x, (int)gridDim.x);
+        if constexpr (CL > 1) cluster_sync_all();  // ... and the one before its CTA may leave
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        tclow_cta_body<CL, kDualFmaThreads, 3>(pt, dual_smem + pf.tensor_smem_offset, (int)blockIdx.x, (int)gridDim.x);
     }
 }
 
@@ -599,6 +657,131 @@ int launch_search_tclow(const float* z, int64_t B, int D, int64_t HW, const floa
     if (stats_out) {
         tclow_stats_kernel<<<1, 1, 0, s>>>(stats_out, count);
         VQB_LAUNCH_CHECK("tclow_stats_kernel");
+    }
+    return VQB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// two engines in one CTA: host side
+// ---------------------------------------------------------------------------
+// images handed to the tensor role.  Measured on B200 (scripts/dual_ab.py, 1M tokens x 16384 codes, D = 4): see the
+// sweep in profiles/; the default is the measured optimum.
+VQB_KNOB g_dual_permille = 500;
+#ifdef VQB_EXPERIMENTAL
+void set_dual_permille(int v) { g_dual_permille = v; }
+#endif
+
+static int64_t dual_tensor_images(int64_t B) {
+    int64_t bt = (B * g_dual_permille + 500) / 1000;
+    return bt < 1 ? 1 : (bt > B - 1 ? B - 1 : bt);
+}
+
+size_t search_dual_workspace_bytes(int64_t B, int D, int64_t HW, int K) {
+    if (!dual_eligible(B, D)) return 0;
+    return search_tclow_workspace_bytes(dual_tensor_images(B) * HW, D, K);
+}
+
+__global__ void dual_stats_kernel(int64_t* stats, const int32_t* list_count, int64_t tensor_tokens) {
+    stats[0] = *list_count;
+    stats[1] = VQB_ALGO_DUAL_LOWD;
+    stats[2] = 0;
+    stats[3] = tensor_tokens;
+}
+
+int launch_search_dual(const float* z, int64_t B, int D, int64_t HW, const float* E, int K, const void* pack,
+                       int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes, int64_t* stats_out, cudaStream_t s) {
+    constexpr int DD = kDualD;
+    constexpr int CL = 2;
+    const int64_t Bt = dual_tensor_images(B);
+    const int64_t Nt = Bt * HW, Nf = (B - Bt) * HW;
+    const LowWorkspace w = low_workspace(Nt, D);
+    if (!ws || ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 255u) != 0) {
+        set_error("two-engine search workspace too small or misaligned: %zu < %zu", ws_bytes, w.total);
+        return VQB_ERR_WORKSPACE;
+    }
+    const PackLayout L = pack_layout(K, D);
+    unsigned char* wsb = static_cast<unsigned char*>(ws);
+    const unsigned char* pk = static_cast<const unsigned char*>(pack);
+    float* img = reinterpret_cast<float*>(wsb + w.off_img);
+    float4* tok_norms = reinterpret_cast<float4*>(wsb + w.off_tau);
+    int32_t* chunk = reinterpret_cast<int32_t*>(wsb + w.off_chunk);
+    int32_t* list = reinterpret_cast<int32_t*>(wsb + w.off_list);
+    int32_t* count = reinterpret_cast<int32_t*>(wsb + w.off_count);
+    const unsigned n_m_tiles = (unsigned)((Nt + kLowRows - 1) / kLowRows);
+    VQB_CUDA_TRY(cudaMemsetAsync(count, 0, sizeof(int32_t), s));
+    split_tf32_tokens_kernel<DD><<<n_m_tiles, 128, 0, s>>>(z, Nt, HW, reinterpret_cast<const int*>(pk), img, tok_norms);
+    VQB_LAUNCH_CHECK("split_tf32_tokens_kernel");
+
+    LowParams p;
+    p.N = Nt;
+    p.K = K;
+    p.Kpad = L.Kpad;
+    p.steps = tclow_steps(D);
+    p.a_img = img;
+    p.b_img = reinterpret_cast<const float*>(pk + L.off_img);
+    p.header = reinterpret_cast<const int*>(pk);
+    p.tok_norms = tok_norms;
+    p.cmax = reinterpret_cast<const float*>(pk + L.off_cmax);
+    p.chunk = chunk;
+    p.list = list;
+    p.list_count = count;
+    p.share_sm = 1;
+    const size_t tile_bytes = (size_t)p.steps * (kLowRows * 32);
+    int stages = kLowMaxStages;
+    const int n_n_tiles = p.Kpad / kLowBN;
+    if (stages > n_n_tiles) stages = n_n_tiles;
+    if (stages < 2) stages = 2;
+    p.n_stages = stages;
+    const size_t fma_smem = round_up_z(LowDCfg<DD, 0>::kSmemBytes, 1024);
+    const size_t tc_smem = 1024 + (2 + (size_t)stages) * tile_bytes + 512 + 2 * kLowRows * 4 * sizeof(float);
+    const size_t smem = fma_smem + tc_smem;
+
+    DualFmaParams pf;
+    pf.z = z + Nt * D;  // images [Bt, B): the latent is [B, D, HW]
+    pf.N = Nf;
+    pf.HW = HW;
+    pf.K = K;
+    pf.pack = pk;
+    pf.L = L;
+    pf.idx_out = idx_out + Nt;
+    pf.dmin_out = dmin_out ? dmin_out + Nt : nullptr;
+    pf.tensor_smem_offset = (uint32_t)fma_smem;
+
+    auto kernel = search_dual_kernel<DD, CL>;
+    VQB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = sm_count() / CL * CL;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kDualThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    VQB_CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
+    if (max_clusters > 0 && grid > max_clusters * CL) {
+        grid = max_clusters * CL;
+        cfg.gridDim = dim3((unsigned)grid);
+    }
+    int64_t per_cta = (Nf + grid - 1) / grid;
+    per_cta = (per_cta + kDualFmaThreads - 1) / kDualFmaThreads * kDualFmaThreads;
+    pf.tokens_per_cta = per_cta;
+    VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, p, pf));
+
+    const unsigned warps = (unsigned)((Nt + 31) / 32);
+    rescore_chunk_kernel<DD><<<(warps + 7) / 8, 256, 0, s>>>(z, E, reinterpret_cast<const float*>(pk + L.off_half_norm),
+                                                             chunk, Nt, HW, K, idx_out, dmin_out);
+    VQB_LAUNCH_CHECK("rescore_chunk_kernel");
+    // unsure tokens of the tensor role: exact search by the CUDA-core kernel (token-list mode)
+    if (int rc = launch_search_lowd_list(z, Bt, D, HW, K, pack, list, count, idx_out, dmin_out, s)) return rc;
+    if (stats_out) {
+        dual_stats_kernel<<<1, 1, 0, s>>>(stats_out, count, Nt);
+        VQB_LAUNCH_CHECK("dual_stats_kernel");
     }
     return VQB_OK;
 }

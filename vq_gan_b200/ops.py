@@ -32,16 +32,17 @@ def _count(kind: str, kernels: int = 0) -> None:
     LAUNCHES[kind] = LAUNCHES.get(kind, 0) + 1
 
 
-def _search_kernels(D: int, algo: int, N: int = 0, K: int = 0) -> int:
+def _search_kernels(D: int, algo: int, N: int = 0, K: int = 0, B: int = 0) -> int:
     """libvqb200 kernels one vqb_search_f32 call launches (mirrors resolve_algo in vqb_api.cu)."""
     if algo == _cabi.ALGO_AUTO:
-        algo = ((_cabi.ALGO_TCGEN05_TF32X3 if (D >= 5 and N * K >= 1 << 28) else _cabi.ALGO_LOWD_FMA) if D <= 16 else
+        algo = (_cabi.ALGO_DUAL_LOWD if (D == 4 and B >= 16 and N * K >= 1 << 30) else
+                (_cabi.ALGO_TCGEN05_TF32X3 if (D >= 5 and N * K >= 1 << 28) else _cabi.ALGO_LOWD_FMA) if D <= 16 else
                 _cabi.ALGO_TCGEN05_F16 if (16 < D <= 256 and (N == 0 or N * K * D >= 1 << 29))
                 else _cabi.ALGO_FP32_TILE)
     # lowd: search + stats; fp32: search (+ finalize) + stats; tcgen05: split, mma, re-score, finalize, stats
     # tf32x3: split, mma, chunk re-score, list search, stats
     return {_cabi.ALGO_LOWD_FMA: 2, _cabi.ALGO_FP32_TILE: 3, _cabi.ALGO_TCGEN05: 5,
-            _cabi.ALGO_TCGEN05_F16: 6, _cabi.ALGO_TCGEN05_TF32X3: 5}[algo]
+            _cabi.ALGO_TCGEN05_F16: 6, _cabi.ALGO_TCGEN05_TF32X3: 5, _cabi.ALGO_DUAL_LOWD: 5}[algo]
 
 
 def _p(t: Optional[Tensor]):
@@ -103,30 +104,6 @@ def prepare_codebook(weight: Tensor) -> Tensor:
         return _prepare(weight.contiguous())
 
 
-_AUX_STREAMS = {}
-DUAL_TENSOR_IMAGES = -1  # images handed to the tensor engine by the two-engine search (-1 = library default)
-
-
-def _aux_stream(device) -> "torch.cuda.Stream":
-    """One side stream per device for the two-engine search (the C ABI takes both streams explicitly)."""
-    key = device.index if device.index is not None else torch.cuda.current_device()
-    st = _AUX_STREAMS.get(key)
-    if st is None:
-        st = _AUX_STREAMS[key] = torch.cuda.Stream(device=device)
-    return st
-
-
-def _dual_eligible(algo: int, B: int, D: int, HW: int, K: int) -> bool:
-    """Experiment only (algo 6, measurement build): never chosen automatically -- on B200 the two kernels do not
-    become co-resident, so the two-engine search is no faster than the CUDA-core kernel alone."""
-    if algo != _cabi.ALGO_DUAL_LOWD:
-        return False
-    import os
-    if os.environ.get("VQB200_EXPERIMENTAL") != "1":
-        raise RuntimeError("ALGO_DUAL_LOWD lives in the measurement build: set VQB200_EXPERIMENTAL=1 (libvqb200_bench.so)")
-    return True
-
-
 def _search_into(z: Tensor, weight: Tensor, algo: int, want_dmin: bool, pack: Optional[Tensor] = None):
     B, D, HW, K = _shape_bdhw(z, weight)
     dev = z.device
@@ -137,30 +114,15 @@ def _search_into(z: Tensor, weight: Tensor, algo: int, want_dmin: bool, pack: Op
     idx = torch.empty((B,) + tuple(z.shape[2:]), dtype=torch.int64, device=dev)
     dmin = torch.empty(idx.shape, dtype=torch.float32, device=dev) if want_dmin else None
     stats = torch.empty(4, dtype=torch.int64, device=dev)  # every search path writes all four entries
-    dual = _dual_eligible(algo, B, D, HW, K)
-    if dual:
-        if D > 4 or B < 2:
-            raise RuntimeError("ALGO_DUAL_LOWD needs D <= 4 and at least 2 images")
-        ws_bytes = lib().vqb_search_dual_workspace_bytes(B, D, HW, K, DUAL_TENSOR_IMAGES)
-    else:
-        ws_bytes = lib().vqb_search_workspace_bytes(B, D, HW, K, algo)
+    ws_bytes = lib().vqb_search_workspace_bytes(B, D, HW, K, algo)
     ws = _bytes(ws_bytes, dev)
     prof = PROFILE
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    if dual:
-        aux = _aux_stream(dev)
-        check(lib().vqb_search_dual_f32(_p(z), B, D, HW, _p(weight), K, _p(pack), _p(idx), _p(dmin), _p(ws), ws_bytes,
-                                        DUAL_TENSOR_IMAGES, _p(stats), _stream(), ctypes.c_void_p(aux.cuda_stream)),
-              "vqb_search_dual_f32")
-        # the workspace and inputs are also used on the side stream: keep the caching allocator from recycling them
-        # for other streams before the join (the join orders everything back onto the current stream)
-        _count("search", 7)
-    else:
-        check(lib().vqb_search_f32(_p(z), B, D, HW, _p(weight), K, _p(pack), _p(idx), _p(dmin), _p(ws),
-                                   ws_bytes, algo, _p(stats), _stream()), "vqb_search_f32")
-        _count("search", _search_kernels(D, algo, B * HW, K))
+    check(lib().vqb_search_f32(_p(z), B, D, HW, _p(weight), K, _p(pack), _p(idx), _p(dmin), _p(ws),
+                               ws_bytes, algo, _p(stats), _stream()), "vqb_search_f32")
+    _count("search", _search_kernels(D, algo, B * HW, K, B))
     if prof is not None:
         ev1.record()
         prof.append((ev0, ev1))

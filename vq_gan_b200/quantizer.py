@@ -27,7 +27,8 @@ class VectorQuantizer(nn.Module):
         lazy_stats: keep the two logged losses as 0-dim device tensors instead of
             Python floats (skips the host sync of quantizer.py:106-107)
         algo: search kernel override (0 auto, 1 low-D FMA, 2 fp32 tile, 3 tcgen05 bf16x3,
-            4 tcgen05 single fp16 pass + exact fp32 re-score, 5 tcgen05 tf32x3 for D <= 16)
+            4 tcgen05 single fp16 pass + exact fp32 re-score, 5 tcgen05 tf32x3 for D <= 16,
+            6 CUDA-core + tf32x3 tensor roles in one CTA for D == 4)
     """
 
     def __init__(self, num_embeddings: int, embedding_dim: int, commitment_cost: float = 0.25, *,
