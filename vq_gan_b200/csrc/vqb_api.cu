@@ -103,6 +103,10 @@ extern "C" int vqb_tune(const char* key, int value) {
         set_dual_permille(value);
         return VQB_OK;
     }
+    if (strcmp(key, "tc16_branchy") == 0 && (value == 0 || value == 1)) {
+        set_tc16_cluster(16 + value);
+        return VQB_OK;
+    }
     if (strcmp(key, "tc16_cluster") == 0 && (value == 1 || value == 2 || value == 4)) {
         set_tc16_cluster(value);
         return VQB_OK;

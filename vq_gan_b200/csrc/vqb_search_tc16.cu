@@ -184,7 +184,9 @@ __device__ __forceinline__ void top4_insert(Top4& g, float v, int i) {
 // token tiles but sweep the codebook in lockstep: each CTA fetches 1/CL of every B stage and TMA
 // multicasts it to all of them, so the L2 -> SM operand traffic (the limiter of the single-pass
 // kernel: 32 KB of B per 512 tensor cycles per SM) drops by CL.
-template <int NKB, int CL>
+// BR: the sorted insert runs only when the group key beats the current fourth-best (a warp-divergent branch taken by
+// ~14 % of the warp-steps: the probability that group n of a token enters its top-4 is 4/n) instead of unconditionally
+template <int NKB, int CL, bool BR = false>
 __global__ void __launch_bounds__(kT16Threads, 1)
     search_tc16_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_e,
                        T16Params p) {
@@ -383,13 +385,15 @@ __global__ void __launch_bounds__(kT16Threads, 1)
                             const uint32_t gid = id_base + (uint32_t)((c0 >> 2) + c4);
                             const float key = __uint_as_float((__float_as_uint(gm) & 0xffffff00u) | gid);
                             // sorted insert of key into (k1 <= k2 <= k3 <= k4)
-                            const float n2 = fminf(k2, fmaxf(k1, key));
-                            const float n3 = fminf(k3, fmaxf(k2, key));
-                            const float n4 = fminf(k4, fmaxf(k3, key));
-                            k1 = fminf(k1, key);
-                            k2 = n2;
-                            k3 = n3;
-                            k4 = n4;
+                            if (!BR || key < k4) {
+                                const float n2 = fminf(k2, fmaxf(k1, key));
+                                const float n3 = fminf(k3, fmaxf(k2, key));
+                                const float n4 = fminf(k4, fmaxf(k3, key));
+                                k1 = fminf(k1, key);
+                                k2 = n2;
+                                k3 = n3;
+                                k4 = n4;
+                            }
                         }
                     }
                     tc_fence_before();
@@ -695,15 +699,18 @@ size_t search_tc16_workspace_bytes(int64_t n_tokens, int D, int K) {
 }
 
 VQB_KNOB g_tc16_cluster = 2;
+VQB_KNOB g_tc16_branchy = 0;  // vqb_tune "tc16_branchy": conditional top-4 insert in the epilogue (cluster 2 only)
 #ifdef VQB_EXPERIMENTAL
-void set_tc16_cluster(int c) { g_tc16_cluster = c; }
+void set_tc16_cluster(int c) {
+    if (c >= 16) g_tc16_branchy = c - 16; else g_tc16_cluster = c;
+}
 #endif
 
-template <int NKB, int CL>
+template <int NKB, int CL, bool BR = false>
 static int launch_tc16_cl(const CUtensorMap& mz, const CUtensorMap& me, const T16Params& p, cudaStream_t s) {
     constexpr int kStages = tc16_stages(NKB);
     const size_t smem = 1024 + NKB * kTcABlockBytes + (size_t)kStages * kTcBStageBytes + kTcBarrierBytes + 12288;
-    VQB_CUDA_TRY(cudaFuncSetAttribute(search_tc16_kernel<NKB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VQB_CUDA_TRY(cudaFuncSetAttribute(search_tc16_kernel<NKB, CL, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     const int n_m_tiles = (int)((p.N + kTcBM - 1) / kTcBM);
     int grid = n_m_tiles < sm_count() ? n_m_tiles : sm_count();
@@ -725,13 +732,13 @@ static int launch_tc16_cl(const CUtensorMap& mz, const CUtensorMap& me, const T1
         // persistent kernel: never launch more clusters than can be co-resident (GPC granularity
         // strands some SMs for larger clusters)
         int max_clusters = 0;
-        VQB_CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, search_tc16_kernel<NKB, CL>, &cfg));
+        VQB_CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, search_tc16_kernel<NKB, CL, BR>, &cfg));
         if (max_clusters > 0 && grid > max_clusters * CL) {
             grid = max_clusters * CL;
             cfg.gridDim = dim3((unsigned)grid);
         }
     }
-    VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_tc16_kernel<NKB, CL>, mz, me, p));
+    VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_tc16_kernel<NKB, CL, BR>, mz, me, p));
     return VQB_OK;
 }
 
@@ -741,7 +748,8 @@ static int launch_tc16_t(const CUtensorMap& mz, const CUtensorMap& me1, const CU
     switch (g_tc16_cluster) {
         case 1: return launch_tc16_cl<NKB, 1>(mz, me1, p, s);
         case 4: return launch_tc16_cl<NKB, 4>(mz, me4, p, s);
-        default: return launch_tc16_cl<NKB, 2>(mz, me2, p, s);
+        default:
+            return g_tc16_branchy ? launch_tc16_cl<NKB, 2, true>(mz, me2, p, s) : launch_tc16_cl<NKB, 2, false>(mz, me2, p, s);
     }
 }
 
