@@ -79,6 +79,15 @@ def _worker(rank, world, port, q):
             idx2, _ = vdist.sharded_search_dp(zr.to(dev), E[klo:khi].contiguous().to(dev), klo)
             want2, _, _ = ops.search(zr.to(dev), E.to(dev))
             out[f"sharded_dp_d{D}"] = bool(torch.equal(idx2, want2))
+            # the bulk-encode pipeline (all-gather of batch i+1 under the search of batch i) returns the same winners
+            batches = [torch.randn(2, D, 16, 16, generator=torch.Generator().manual_seed(40 + 10 * j + rank)).to(dev)
+                       for j in range(3)]
+            enc = vdist.ShardedEncoder(E[klo:khi].contiguous().to(dev), klo)
+            got = [i for i, _ in enc.encode_all(batches)]
+            want = [ops.search(b, E.to(dev))[0] for b in batches]
+            out[f"sharded_encoder_d{D}"] = len(got) == 3 and all(torch.equal(a, b) for a, b in zip(got, want))
+            idx_c, _ = vdist.sharded_search_dp(zr.to(dev), E[klo:khi].contiguous().to(dev), klo, chunks=2)
+            out[f"sharded_dp_chunked_d{D}"] = bool(torch.equal(idx_c, want2))
             # a NaN code on the LAST shard wins everywhere, like the unsharded ATen argmin (quantizer.py:76)
             En = torch.randn(K, D, generator=torch.Generator().manual_seed(11))
             En[K - 5, 1] = float("nan")

@@ -749,7 +749,10 @@ static int launch_tc16_t(const CUtensorMap& mz, const CUtensorMap& me1, const CU
         case 1: return launch_tc16_cl<NKB, 1>(mz, me1, p, s);
         case 4: return launch_tc16_cl<NKB, 4>(mz, me4, p, s);
         default:
-            return g_tc16_branchy ? launch_tc16_cl<NKB, 2, true>(mz, me2, p, s) : launch_tc16_cl<NKB, 2, false>(mz, me2, p, s);
+#ifdef VQB_EXPERIMENTAL  // measured slower (4.82 vs 4.32 ms at D=64, 7.56 vs 7.26 at D=256): measurement build only
+            if (g_tc16_branchy) return launch_tc16_cl<NKB, 2, true>(mz, me2, p, s);
+#endif
+            return launch_tc16_cl<NKB, 2, false>(mz, me2, p, s);
     }
 }
 
