@@ -875,7 +875,7 @@ def measure_quantizer(args, workload, world, rank, local_rank, device, peaks, fm
         roofline = {"bound": bound, "kernel": {1: "search_lowd_kernel", 2: "search_fp32_kernel",
                                                3: "search_tc_kernel", 4: "search_tc16_kernel",
                                                5: "search_tclow_kernel",
-                                               6: "search_lowd_kernel+search_tclow_kernel"}.get(algo, str(algo)),
+                                               6: "search_dual_kernel"}.get(algo, str(algo)),
                     "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                     "traffic": None, "kernel_ms": s_ms, "algorithmic_flops_per_launch": flops,
                     "algorithmic_bytes_per_launch": tokens * (4 * D + 8) + 4 * K * D,

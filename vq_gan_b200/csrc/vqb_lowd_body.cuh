@@ -166,18 +166,22 @@ __device__ __forceinline__ void lowd_segment(LowDCtx<D, V>& c, int64_t seg_base)
 
     float m[T], mprev[T];
     int cid[T];
+    bool any_tok = false;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         m[t] = INFINITY;
         mprev[t] = INFINITY;
         cid[t] = 0;
+        any_tok |= tok[t] >= 0;
     }
+    // a warp without tokens (the tail of a range, most warps of a list-mode CTA) only keeps the barriers company
+    const bool warp_live = __ballot_sync(0xffffffffu, any_tok) != 0;
 
     for (int tile = 0; tile < c.n_tiles; ++tile) {
         const uint32_t v = c.visit;
         const float* buf = c.smem_tiles + (v & 1) * Cfg::kTileFloats;
         mbar_wait(c.bars + (v & 1), (v >> 1) & 1);
-        const int chunks = tile_codes<D, V>(c, tile) / kChunkCodes;
+        const int chunks = warp_live ? tile_codes<D, V>(c, tile) / kChunkCodes : 0;
         const float* hbuf = buf + Cfg::kTileCodes * D;
         for (int ch = 0; ch < chunks; ++ch) {
             const float* ep = buf + (size_t)ch * kChunkCodes * D;
@@ -206,6 +210,7 @@ __device__ __forceinline__ void lowd_segment(LowDCtx<D, V>& c, int64_t seg_base)
         if (tid == 0 && v + 2 < c.total_visits) issue_visit<D, V>(c, v + 2);
     }
 
+    if (!warp_live) return;
     // ---- resolve the index: the warp re-scores chunk cid[t] of each token ----
     int best[T];
 #pragma unroll
@@ -282,8 +287,10 @@ __device__ __forceinline__ void lowd_cta_body(const float* __restrict__ z, int64
     c.list = list;
     if constexpr (kList) {  // the number of flagged tokens is only known on the device
         N = *list_count;
+        // a list is short (a few thousand unsure tokens): spread it over ALL CTAs in whole warps instead of filling
+        // a dozen CTAs with 256 tokens each (measured 195 us per call at C2 before, latency of 12 busy SMs)
         tokens_per_cta = (N + n_ctas - 1) / n_ctas;
-        tokens_per_cta = (tokens_per_cta + kLowDThreads - 1) / kLowDThreads * kLowDThreads;
+        tokens_per_cta = (tokens_per_cta + 31) / 32 * 32;
     }
     c.N = N;
     c.g_pairs = reinterpret_cast<const float*>(pack + L.off_pairs);
