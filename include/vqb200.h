@@ -170,6 +170,19 @@ VQB_API int vqb_conv1x1_f32(const float* x, int64_t B, int Cin, int64_t HW, cons
                     const float* bias, int Cout, float* y, void* workspace, size_t workspace_bytes,
                     int algo, vqb_stream_t stream);
 
+/* ---- encoder tail / decoder tail normalisation + activation (next row N2) ---------------
+ * `h = norm_out(h); h = F.silu(h)` (encoder_decoder.py:166-167 and 249-250; nn.GroupNorm(groups, C, eps, affine)):
+ *   y[b,c,hw] = silu((x - mean[b,g]) * rstd[b,g] * gamma[c] + beta[c]),  g = c / (C / groups)
+ * in one pass over HBM (the group is staged in shared memory when (C/groups)*HW <= 48 Ki floats).  mean_out / rstd_out
+ * [B*groups] are saved for the backward, which returns dx and ACCUMULATES dgamma[C] / dbeta[C] (nullable). */
+VQB_API int vqb_groupnorm_silu_f32(const float* x, int64_t B, int C, int64_t HW, const float* gamma,
+                           const float* beta, int groups, float eps, float* y, float* mean_out,
+                           float* rstd_out, vqb_stream_t stream);
+VQB_API int vqb_groupnorm_silu_backward_f32(const float* dy, const float* x, int64_t B, int C, int64_t HW,
+                                    const float* gamma, const float* beta, int groups, const float* mean,
+                                    const float* rstd, float* dx, float* dgamma_accum, float* dbeta_accum,
+                                    vqb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

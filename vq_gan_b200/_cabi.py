@@ -51,6 +51,10 @@ PROTOTYPES = {
     "vqb_conv1x1_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vqb_conv1x1_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p,
                                 c_void_p, c_size_t, c_int, c_void_p]),
+    "vqb_groupnorm_silu_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_float, c_void_p,
+                                       c_void_p, c_void_p, c_void_p]),
+    "vqb_groupnorm_silu_backward_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int,
+                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 # measurement build (include/vqb200_bench.h): everything above plus the experiment knobs / microbenchmarks

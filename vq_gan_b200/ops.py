@@ -545,6 +545,80 @@ def _conv1x1_bwd(ctx, gy):
 torch.library.register_autograd("vqb200::conv1x1", _conv1x1_bwd, setup_context=_conv1x1_setup)
 
 
+# ---------------------------------------------------------------------------
+# GroupNorm + SiLU in front of the convolutions either side of the path (row N2; encoder_decoder.py:166-167, 249-250)
+# ---------------------------------------------------------------------------
+@torch.library.custom_op("vqb200::groupnorm_silu", mutates_args=())
+def groupnorm_silu(x: Tensor, weight: Tensor, bias: Tensor, num_groups: int, eps: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """(y, mean[B*G], rstd[B*G]) with y = silu(group_norm(x, num_groups, weight, bias, eps)); x is [B, C, *spatial]."""
+    _need_cuda_f32(x, "x")
+    _need_cuda_f32(weight, "weight")
+    _need_cuda_f32(bias, "bias")
+    x = x.contiguous()
+    if x.dim() < 2 or int(x.shape[1]) % int(num_groups) != 0 or weight.numel() != x.shape[1] or bias.numel() != x.shape[1]:
+        raise RuntimeError(f"groupnorm_silu: {tuple(x.shape)} channels do not match {num_groups} groups / the affine parameters")
+    B, C = int(x.shape[0]), int(x.shape[1])
+    HW = x.numel() // max(B * C, 1)
+    y = torch.empty_like(x)
+    mean = torch.empty(B * num_groups, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(B * num_groups, dtype=torch.float32, device=x.device)
+    if x.numel() == 0:
+        return y, mean, rstd
+    with _on(x.device):
+        check(lib().vqb_groupnorm_silu_f32(_p(x), B, C, HW, _p(weight.contiguous()), _p(bias.contiguous()), int(num_groups),
+                                           float(eps), _p(y), _p(mean), _p(rstd), _stream()), "vqb_groupnorm_silu_f32")
+        _count("keys")
+    return y, mean, rstd
+
+
+@groupnorm_silu.register_fake
+def _(x, weight, bias, num_groups, eps):
+    return torch.empty_like(x), x.new_empty((x.shape[0] * num_groups,)), x.new_empty((x.shape[0] * num_groups,))
+
+
+@torch.library.custom_op("vqb200::groupnorm_silu_backward", mutates_args=())
+def groupnorm_silu_backward(gy: Tensor, x: Tensor, weight: Tensor, bias: Tensor, mean: Tensor, rstd: Tensor,
+                            num_groups: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """(dx, dweight, dbias)."""
+    gy = gy.contiguous().to(torch.float32)
+    x = x.contiguous()
+    B, C = int(x.shape[0]), int(x.shape[1])
+    HW = x.numel() // max(B * C, 1)
+    dx = torch.empty_like(x)
+    dw = torch.zeros(C, dtype=torch.float32, device=x.device)
+    db = torch.zeros(C, dtype=torch.float32, device=x.device)
+    if x.numel() == 0:
+        return dx, dw, db
+    with _on(x.device):
+        check(lib().vqb_groupnorm_silu_backward_f32(_p(gy), _p(x), B, C, HW, _p(weight.contiguous()), _p(bias.contiguous()),
+                                                    int(num_groups), _p(mean), _p(rstd), _p(dx), _p(dw), _p(db), _stream()),
+              "vqb_groupnorm_silu_backward_f32")
+        _count("keys")
+    return dx, dw, db
+
+
+@groupnorm_silu_backward.register_fake
+def _(gy, x, weight, bias, mean, rstd, num_groups):
+    return torch.empty_like(x), torch.empty_like(weight), torch.empty_like(bias)
+
+
+def _gn_setup(ctx, inputs, output):
+    x, weight, bias, num_groups, _eps = inputs
+    ctx.save_for_backward(x, weight, bias, output[1], output[2])
+    ctx.num_groups = num_groups
+    ctx.mark_non_differentiable(output[1], output[2])
+
+
+def _gn_bwd(ctx, gy, g_mean, g_rstd):
+    x, weight, bias, mean, rstd = ctx.saved_tensors
+    dx, dw, db = groupnorm_silu_backward(gy, x, weight, bias, mean, rstd, ctx.num_groups)
+    return (dx if ctx.needs_input_grad[0] else None, dw if ctx.needs_input_grad[1] else None,
+            db if ctx.needs_input_grad[2] else None, None, None)
+
+
+torch.library.register_autograd("vqb200::groupnorm_silu", _gn_bwd, setup_context=_gn_setup)
+
+
 def fma_peak_tflops(packed: bool, iters: int = 4096, repeats: int = 5) -> float:
     """Measured FP32 FMA peak of the current device (roofline denominator for the
     low-D search): best of `repeats`, CUDA events on the current stream."""

@@ -142,6 +142,31 @@ class QuantConv1x1(nn.Conv2d):
         return ops.conv1x1(x, self.weight, self.bias, self.algo)
 
 
+class GroupNormSiLU(nn.GroupNorm):
+    """`h = norm_out(h); h = F.silu(h)` of the reference Encoder / Decoder (encoder_decoder.py:166-167, 249-250) as ONE
+    kernel (next row N2): same constructor, parameters and state_dict keys as the `nn.GroupNorm(32, C, eps=1e-6)` it
+    replaces, but `forward` returns the ACTIVATED tensor, so the `F.silu` line that follows it in the reference
+    `forward` must go.  Forward and backward run on `vqb_groupnorm_silu[_backward]_f32`; the
+    3x3 convolution that follows stays a cuDNN call."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not self.affine:
+            raise RuntimeError("GroupNormSiLU needs affine=True (the reference's norm_out is affine)")
+        if x.dtype != torch.float32:
+            x = x.float()
+        y, _, _ = ops.groupnorm_silu(x, self.weight, self.bias, self.num_groups, float(self.eps))
+        return y
+
+
+def encoder_tail(encoder: nn.Module, h: torch.Tensor) -> torch.Tensor:
+    """The last three lines of the reference `Encoder.forward` / `Decoder.forward` (encoder_decoder.py:166-168,
+    249-251 before the sigmoid): `conv_out(silu(norm_out(h)))` with the normalisation + activation fused.  Uses the
+    module's own `norm_out` / `conv_out` parameters (any `nn.GroupNorm` / `nn.Conv2d`)."""
+    gn = encoder.norm_out
+    y, _, _ = ops.groupnorm_silu(h.float(), gn.weight, gn.bias, gn.num_groups, float(gn.eps))
+    return encoder.conv_out(y)
+
+
 class EMAVectorQuantizer(VectorQuantizer):
     """Extension (no reference code; semantics of the VQ-VAE paper, appendix A.1 -- PARITY UNPINNED):
     the codebook is updated by exponential moving averages of the per-code token counts and sums instead
