@@ -127,3 +127,38 @@ def test_sharded_argmin_key_orders_like_aten_argmin():
     # two NaN scores on different shards: the lower global index wins
     k = orc.argmin_key(torch.tensor([float("nan"), float("nan")]), torch.tensor([700, 12]))
     assert int(k.min() & 0xFFFFFFFF) == 12
+
+
+def test_loss_dict_is_a_dict_of_floats_on_every_read_path():
+    """`LossDict`: the logged floats of quantizer.py:106-107 are fetched at first use; whatever way the dict is read,
+    the caller sees what the reference returns (a dict with one tensor and two Python floats)."""
+    import copy
+    import pickle
+    from vq_gan_b200 import LossDict
+
+    def fresh():
+        return LossDict(torch.tensor(1.25), torch.tensor(0.5))   # CPU tensors stand in for the device scalars
+
+    want = {"vq_loss": torch.tensor(1.25), "codebook_loss": 0.5, "commitment_loss": 0.5}
+    d = fresh()
+    assert isinstance(d, dict) and list(d) == ["vq_loss", "codebook_loss", "commitment_loss"] and len(d) == 3
+    assert d._pending is not None                      # nothing read yet: no sync happened in "forward"
+    assert d["vq_loss"].item() == 1.25 and d._pending is not None
+    assert d["codebook_loss"] == 0.5 and isinstance(d["codebook_loss"], float) and d._pending is None
+    for read in (lambda x: dict(x), lambda x: {**x}, lambda x: x.copy(), lambda x: dict(x.items()),
+                 lambda x: copy.copy(x), lambda x: pickle.loads(pickle.dumps(x)), lambda x: {k: x.get(k) for k in x}):
+        got = read(fresh())
+        assert type(got["commitment_loss"]) is float and got["commitment_loss"] == 0.5, read
+        assert set(got) == set(want)
+    assert list(fresh().values())[1:] == [0.5, 0.5]
+    plain = {}
+    plain.update(fresh())
+    assert plain["codebook_loss"] == 0.5
+    assert "0.5" in repr(fresh())
+    # VQVAE.forward adds a key (vq_vae.py:158); user code may overwrite the logged ones
+    d = fresh()
+    d["codebook_usage_ratio"] = 0.75
+    assert d["codebook_usage_ratio"] == 0.75 and d["commitment_loss"] == 0.5
+    d = fresh()
+    d["codebook_loss"] = 9.0
+    assert d["codebook_loss"] == 9.0 and d["commitment_loss"] == 0.5

@@ -10,8 +10,8 @@ from ._cabi import (ALGO_AUTO, ALGO_FP32_TILE, ALGO_LOWD_FMA, ALGO_TCGEN05, ALGO
                     LIB_PATH,
                     VqbError, lib)
 from . import ops
-from .quantizer import EMAVectorQuantizer, GroupNormSiLU, QuantConv1x1, VectorQuantizer, encoder_tail
+from .quantizer import EMAVectorQuantizer, GroupNormSiLU, LossDict, QuantConv1x1, VectorQuantizer, encoder_tail
 
-__all__ = ["VectorQuantizer", "EMAVectorQuantizer", "QuantConv1x1", "GroupNormSiLU", "encoder_tail", "ops", "lib", "LIB_PATH", "VqbError", "ALGO_AUTO", "ALGO_LOWD_FMA",
+__all__ = ["VectorQuantizer", "EMAVectorQuantizer", "QuantConv1x1", "GroupNormSiLU", "encoder_tail", "LossDict", "ops", "lib", "LIB_PATH", "VqbError", "ALGO_AUTO", "ALGO_LOWD_FMA",
            "ALGO_FP32_TILE", "ALGO_TCGEN05", "ALGO_TCGEN05_F16", "ALGO_TCGEN05_TF32X3"]
 __version__ = "0.1.0"

@@ -14,6 +14,91 @@ from . import ops
 from ._cabi import ALGO_AUTO, ALGO_NAMES
 
 
+_LOGGED = ("codebook_loss", "commitment_loss")
+
+
+class LossDict(dict):
+    """The `loss_dict` of quantizer.py:104-108 -- `{'vq_loss': Tensor, 'codebook_loss': float, 'commitment_loss':
+    float}`, a real `dict` -- whose two logged floats are read from the device WHEN THEY ARE FIRST LOOKED AT instead
+    of inside `forward`.  The reference calls `.item()` twice per forward (quantizer.py:106-107), which stalls the
+    host until the search has finished and leaves the GPU idle while Python launches the backward pass; a training
+    loop that only logs every N steps (or never reads these two keys, like train_vqgan.py:303-315, which shows
+    `vq_loss` and the usage ratio) then never pays that stall.  Every read path -- `d[k]`, `get`, `items`, `values`,
+    `copy`, `{**d}`, `dict(d)`, `repr`, `==`, pickling -- sees plain Python floats."""
+
+    __slots__ = ("_pending",)
+
+    def __init__(self, vq_loss, mse_device):
+        super().__init__(vq_loss=vq_loss, codebook_loss=None, commitment_loss=None)
+        self._pending = mse_device  # 0-dim device tensor, or None once the floats are in place
+
+    def _materialize(self):
+        p = self._pending
+        if p is not None:
+            self._pending = None
+            v = p.item()  # the one device->host sync, at first use
+            for k in _LOGGED:
+                if dict.__getitem__(self, k) is None:
+                    dict.__setitem__(self, k, v)
+
+    def __getitem__(self, key):
+        if key in _LOGGED:
+            self._materialize()
+        return dict.__getitem__(self, key)
+
+    def __setitem__(self, key, value):
+        if key in _LOGGED and self._pending is not None:
+            self._materialize()
+        dict.__setitem__(self, key, value)
+
+    def __iter__(self):  # a Python-level __iter__ also keeps dict.update / dict(d) / {**d} off CPython's raw-storage fast path
+        return dict.__iter__(self)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def pop(self, key, *default):
+        self._materialize()
+        return dict.pop(self, key, *default)
+
+    def popitem(self):
+        self._materialize()
+        return dict.popitem(self)
+
+    def setdefault(self, key, default=None):
+        self._materialize()
+        return dict.setdefault(self, key, default)
+
+    def items(self):
+        self._materialize()
+        return dict.items(self)
+
+    def values(self):
+        self._materialize()
+        return dict.values(self)
+
+    def copy(self):
+        self._materialize()
+        return dict(dict.items(self))
+
+    def __eq__(self, other):
+        self._materialize()
+        return dict.__eq__(self, other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        self._materialize()
+        return dict.__repr__(self)
+
+    def __reduce__(self):
+        self._materialize()
+        return (dict, (dict(dict.items(self)),))
+
+
 class VectorQuantizer(nn.Module):
     """Nearest-codebook bottleneck (reference: quantizer.py:17-149).
 
@@ -25,7 +110,7 @@ class VectorQuantizer(nn.Module):
         return_format: "reference" -> (z_q, loss_dict, indices) as quantizer.py:110;
             "taming" -> (z_q, vq_loss, (perplexity, None, indices)) -- values parity-unpinned
         lazy_stats: keep the two logged losses as 0-dim device tensors instead of
-            Python floats (skips the host sync of quantizer.py:106-107)
+            Python floats (never syncs; the default returns a `LossDict` whose floats sync on first access)
         algo: search kernel override (0 auto, 1 low-D FMA, 2 fp32 tile, 3 tcgen05 bf16x3,
             4 tcgen05 single fp16 pass + exact fp32 re-score, 5 tcgen05 tf32x3 for D <= 16,
             6 CUDA-core + tf32x3 tensor roles in one CTA for D == 4)
@@ -73,8 +158,8 @@ class VectorQuantizer(nn.Module):
             m = mse.detach()
             loss_dict = {"vq_loss": vq_loss, "codebook_loss": m, "commitment_loss": m}
         else:
-            m = mse.item()  # ONE device->host sync for both logged values
-            loss_dict = {"vq_loss": vq_loss, "codebook_loss": m, "commitment_loss": m}
+            # Python floats like quantizer.py:106-107, read from the device (ONE sync for both) on first access
+            loss_dict = LossDict(vq_loss, mse.detach())
         return z_q, loss_dict, indices
 
     # -- quantizer.py:112-132 --------------------------------------------------
@@ -213,5 +298,7 @@ class EMAVectorQuantizer(VectorQuantizer):
                     sums, counts, _ = ops.stats_unpack(flat, sums.shape, self.num_embeddings, 0, 1.0)
                 ops.ema_update(self.embedding.weight.data, self.cluster_size, self.embed_sum, counts.contiguous(),
                                sums.contiguous(), float(self.decay), float(self.eps))
-        m = mse.detach() if self.lazy_stats else mse.item()
-        return z_q, {"vq_loss": commit, "codebook_loss": m, "commitment_loss": m}, indices
+        if self.lazy_stats:
+            m = mse.detach()
+            return z_q, {"vq_loss": commit, "codebook_loss": m, "commitment_loss": m}, indices
+        return z_q, LossDict(commit, mse.detach()), indices
