@@ -850,7 +850,7 @@ def measure_quantizer(args, workload, world, rank, local_rank, device, peaks, fm
     e1.record()
     barrier()
     losses_read.append(float(loss_host[(3 + e2e_steps - 1) & 1]))   # the last step's loss (its event has completed)
-    assert len(losses_read) - n_read0 == e2e_steps and all(v == v for v in losses_read)
+    assert len(losses_read) - n_read0 == e2e_steps + 1 and all(v == v for v in losses_read)  # + the last warm-up step's
     e2e_ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([e2e_ms], device=device)
