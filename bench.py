@@ -798,8 +798,9 @@ def measure_quantizer(args, workload, world, rank, local_rank, device, peaks, fm
             ev.record(copy_stream)
         return zt, ev
 
-    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()   # ring of two result slots
-    loss_events = [None, None]
+    RING = 4                                                          # result slots: the host consumes step i - (RING - 1)
+    loss_host = torch.zeros(RING, dtype=torch.float32).pin_memory()
+    loss_events = [None] * RING
     losses_read = []
 
     def e2e_step(i, staged):
@@ -818,10 +819,11 @@ def measure_quantizer(args, workload, world, rank, local_rank, device, peaks, fm
             sq = (vq_sync.last_mse * float(z.numel())).reshape(1)   # device value: no pageable H2D copy
             dE, hist, s = vdist.allreduce_stats(weight.grad, usage, sq, average_dE=True)
             weight.grad = dE
-        # the step's results go back to pinned host memory inside the timed region: the loss into a two-slot ring on
-        # the compute stream, the indices on their own stream; the HOST reads the loss of step i-1 here, one step late,
-        # so that it never waits for the GPU while there is nothing queued behind (every step's loss is still read)
-        slot = i & 1
+        # the step's results go back to pinned host memory inside the timed region: the loss into a small ring on the
+        # compute stream, the indices on their own stream; the HOST reads the loss of step i-3 here, so that it never
+        # waits for the GPU while there is nothing queued behind and a late rank's jitter is absorbed by the queue
+        # instead of stalling the all-reduce of every other rank (every step's loss is still read)
+        slot = i % RING
         loss_host[slot:slot + 1].copy_(loss_dict["vq_loss"].detach().reshape(1), non_blocking=True)
         done = torch.cuda.Event()
         done.record()
@@ -830,10 +832,12 @@ def measure_quantizer(args, workload, world, rank, local_rank, device, peaks, fm
             d2h_stream.wait_event(done)
             idx_host.copy_(idx, non_blocking=True)
             idx.record_stream(d2h_stream)
-        prev = loss_events[slot ^ 1]
+        old = (i + 1) % RING                       # the oldest slot = the one the NEXT step will overwrite
+        prev = loss_events[old]
         if prev is not None:
             prev.synchronize()
-            losses_read.append(float(loss_host[slot ^ 1]))
+            losses_read.append(float(loss_host[old]))
+            loss_events[old] = None
         return None, nxt
 
     e2e_steps = max(3, min(steps, 20 if workload != "c3" else 10))
@@ -849,8 +853,12 @@ def measure_quantizer(args, workload, world, rank, local_rank, device, peaks, fm
     torch.cuda.current_stream().wait_stream(d2h_stream)
     e1.record()
     barrier()
-    losses_read.append(float(loss_host[(3 + e2e_steps - 1) & 1]))   # the last step's loss (its event has completed)
-    assert len(losses_read) - n_read0 == e2e_steps + 1 and all(v == v for v in losses_read)  # + the last warm-up step's
+    for k in range(RING):                                            # drain: the last RING-1 steps' losses
+        if loss_events[k] is not None:
+            loss_events[k].synchronize()
+            losses_read.append(float(loss_host[k]))
+            loss_events[k] = None
+    assert len(losses_read) == 3 + e2e_steps and all(v == v for v in losses_read)  # every step's loss reached the host
     e2e_ms = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([e2e_ms], device=device)
@@ -933,7 +941,7 @@ def measure_quantizer(args, workload, world, rank, local_rank, device, peaks, fm
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "VectorQuantizer.forward (reference contract) + backward on pinned host latents; H2D of step i+1 "
                            "overlaps step i on a copy stream; every step's loss and indices are copied to pinned host memory "
-                           "inside the timed region, the host consumes the loss one step late (no stall with an empty queue)"},
+                           "inside the timed region, the host consumes each loss three steps late (no stall with an empty queue)"},
             "gpu_launches": gpu_launches,
             "gpu_launches_note": "host-side count of libvqb200 kernels per entry point (mirrors the dispatch)",
             "hbm_kernels": hbm,
