@@ -46,7 +46,7 @@ extern "C" {
 #define VQB_ALGO_LOWD_FMA 1   /* D <= 16: packed-FFMA2 CUDA-core kernel         */
 #define VQB_ALGO_FP32_TILE 2  /* any D: fp32 register-tiled CUDA-core kernel    */
 #define VQB_ALGO_TCGEN05 3    /* D in {64,128,192,256}: bf16x3 tcgen05/TMEM     */
-#define VQB_ALGO_TCGEN05_F16 4 /* any 16 < D <= 256 (zero-padded to 64-channel blocks): one fp16 tcgen05
+#define VQB_ALGO_TCGEN05_F16 4 /* any 16 < D <= 512 (zero-padded to 64-channel blocks): one fp16 tcgen05
                                  pass, certified candidates re-scored exactly in fp32 */
 #define VQB_ALGO_TCGEN05_TF32X3 5 /* D <= 16: tf32x3 tcgen05 pass, certified 32-code chunk re-scored
                                      with the FMA chain of algo 1 (bit-identical indices) */

@@ -3,8 +3,8 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vq_gan_b200 import ops
 torch.manual_seed(0)
-for D, algos in ((2, (1, 5)), (4, (1, 5)), (8, (1, 5)), (16, (1, 5)), (32, (2,)), (64, (3, 4)), (128, (3, 4)), (192, (4,)), (256, (3, 4))):
-    B = 1024 if D != 32 else 128
+for D, algos in ((2, (1, 5)), (4, (1, 5)), (8, (1, 5)), (16, (1, 5)), (32, (2,)), (64, (3, 4)), (128, (3, 4)), (192, (4,)), (256, (3, 4)), (320, (4,)), (384, (4,)), (512, (2, 4))):
+    B = 1024 if D not in (32, 512) else (128 if D == 32 else 256)
     z = torch.randn(B, D, 32, 32, device="cuda")
     E = torch.randn(16384, D, device="cuda")
     for a in algos:

@@ -48,7 +48,7 @@ def test_lowd_tensor_path_equals_fma_kernel_on_adversarial_data(kind, D, K):
 
 
 @pytest.mark.parametrize("kind", ["grid", "clustered", "scaled", "tiny_codes", "outliers"])
-@pytest.mark.parametrize("D,K", [(32, 1000), (64, 4096), (256, 2048), (100, 777)])
+@pytest.mark.parametrize("D,K", [(32, 1000), (64, 4096), (256, 2048), (100, 777), (320, 1500), (512, 2048), (450, 900)])
 def test_fp16_tensor_path_on_adversarial_data(kind, D, K):
     from vq_gan_b200 import ops
     z, E = _make(kind, D, K, 12000, D * 3 + K)

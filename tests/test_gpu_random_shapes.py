@@ -29,6 +29,9 @@ def _cases():
                     int(rng.integers(0, 1 << 30))))
     # persistent-kernel edge cases: one more tile than SMs (second round with a lone CTA whose cluster
     # partner only pads), ragged last tile, exactly one full wave
+    # 256 < D <= 512: the fp16 tensor kernel with a 80-128 KB resident token tile
+    out += [(320, 1000, 2, 700, 21), (384, 513, 3, 256, 22), (512, 2000, 2, 1024, 23), (450, 300, 1, 999, 24),
+            (512, 256, 149, 128, 25)]
     out += [(64, 300, 149, 128, 11), (4, 300, 149, 128, 12), (8, 257, 149, 128, 13), (256, 256, 297, 64, 14),
             (128, 130, 148, 128, 15), (16, 1000, 2, 9500, 16), (32, 700, 3, 6400, 17)]
     return out
@@ -54,7 +57,7 @@ def test_random_shape_all_kernels_agree(D, K, B, HW, seed):
     algos = [0]
     if D <= 16:
         algos += [1, 5]
-    if 16 < D <= 256:
+    if 16 < D <= 512:
         algos.append(4)
     if D % 64 == 0 and D <= 256:
         algos.append(3)

@@ -251,7 +251,7 @@ extern "C" int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, cons
                                     stats_out, s);
         case VQB_ALGO_TCGEN05_F16:
             if (!tc16_eligible_dim(D)) {
-                set_error("VQB_ALGO_TCGEN05_F16 needs %d < D <= %d, got %d", kLowDMax, kTcMaxD, D);
+                set_error("VQB_ALGO_TCGEN05_F16 needs %d < D <= %d, got %d", kLowDMax, kTc16MaxD, D);
                 return VQB_ERR_UNSUPPORTED;
             }
             return launch_search_tc16(z, B, D, HW, E, K, pack, idx_out, dmin_out, workspace, workspace_bytes,

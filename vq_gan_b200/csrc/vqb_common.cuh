@@ -68,7 +68,8 @@ constexpr int kPadCodes = 256;
 constexpr int kHeaderBytes = 256;
 constexpr int kLowDMax = 16;
 constexpr int kTcMinD = 64;
-constexpr int kTcMaxD = 256;
+constexpr int kTcMaxD = 256;     // bf16x3 kernel (token tile hi + lo resident)
+constexpr int kTc16MaxD = 512;   // fp16 kernel: a 128 x 512 fp16 token tile (128 KB) still leaves two 32 KB codebook stages
 
 __host__ __device__ inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
 __host__ __device__ inline size_t round_up_z(size_t x, size_t m) { return (x + m - 1) / m * m; }
@@ -77,7 +78,7 @@ __host__ __device__ inline bool tc_eligible_dim(int D) {  // bf16x3 kernel: whol
     return D >= kTcMinD && D <= kTcMaxD && (D % 64) == 0;
 }
 // single-pass fp16 kernel: any 16 < D <= 256, the fp16 operand images are zero-padded to 64-channel blocks
-__host__ __device__ inline bool tc16_eligible_dim(int D) { return D > kLowDMax && D <= kTcMaxD; }
+__host__ __device__ inline bool tc16_eligible_dim(int D) { return D > kLowDMax && D <= kTc16MaxD; }
 __host__ __device__ inline int tc16_dpad(int D) { return round_up_i(D, 64); }
 
 struct PackLayout {

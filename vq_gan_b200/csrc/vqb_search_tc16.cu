@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(256)
                           __half* __restrict__ z16, float* __restrict__ inv_scale, float* __restrict__ znorm,
                           float* __restrict__ zres) {
     constexpr int D = 32 * NCH;  // padded row length (multiple of 64); channels >= Dreal are zeros
-    __shared__ float tile[D][33];
+    extern __shared__ float split_smem[];  // [D][33]: 33.8 KB at D = 256, 67.6 KB at D = 512
+    float (*tile)[33] = reinterpret_cast<float (*)[33]>(split_smem);
     __shared__ float part_a[8][32];
     __shared__ float part_b[8][32];
     __shared__ int tok_exp[32];
@@ -147,6 +148,7 @@ struct T16Params {
     int32_t* pair_count;     // statistics only
     int32_t* full_list;      // tokens needing a full fp32 re-score
     int32_t* full_count;
+    float acc_eps;           // relative fp32-accumulation allowance: 2^-15 up to D = 256, 2^-14 above (sums twice as long)
 };
 
 // four smallest group minima of a token and the groups of the best three
@@ -450,13 +452,13 @@ __global__ void __launch_bounds__(kT16Threads, 1)
                 // exceeds m1 by tau = eps(min(n0, max|e|)) + eps(n1) -- the threshold follows the norm of
                 // the WINNER, not the largest norm in the codebook (one outlier code no longer inflates it).
                 const float zn = p.znorm[row], zr = p.zres[row];
-                const float alpha = zr + (zn + zr) * rho16 + (1.f / 32768.f) * zn;
+                const float alpha = zr + (zn + zr) * rho16 + p.acc_eps * zn;
                 const float beta0 = (zn + zr) * a16;
                 const float n1 = fminf(__ldg(p.gmax + m.i1), e_max);
-                const float eps1 = alpha * n1 + beta0 + (1.f / 16384.f) * (0.5f * n1 * n1 + zn * n1);
+                const float eps1 = alpha * n1 + beta0 + 2.f * p.acc_eps * (0.5f * n1 * n1 + zn * n1);
                 const float U = m.v1 + eps1;
                 const float n0 = fminf(zn + sqrtf(fmaxf(zn * zn + 2.f * U, 0.f)), e_max);
-                const float eps0 = alpha * n0 + beta0 + (1.f / 16384.f) * (0.5f * n0 * n0 + zn * n0);
+                const float eps0 = alpha * n0 + beta0 + 2.f * p.acc_eps * (0.5f * n0 * n0 + zn * n0);
                 const float tau = 1.0001f * (eps0 + eps1);
                 const bool only1 = (m.v2 - m.v1) > tau;  // every candidate is in group 1
                 const bool only2 = (m.v3 - m.v1) > tau;  // ... in groups 1-2
@@ -508,7 +510,8 @@ __global__ void __launch_bounds__(256)
     constexpr int DT = 32 * NCH;  // D rounded up to 32; tile rows >= D are zeros
     const int D = kExact ? DT : Dreal;  // a compile-time constant in the exact instantiations
     // row stride 36 floats: the 4 tokens of a warp are one aligned 16-byte read, stores stay conflict-free
-    __shared__ __align__(16) float tile[DT][36];
+    extern __shared__ __align__(16) float rescore_smem[];  // [DT][36]: 36.9 KB at D = 256, 73.7 KB at D = 512
+    float (*tile)[36] = reinterpret_cast<float (*)[36]>(rescore_smem);
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t t0 = (int64_t)blockIdx.x * 32;
     {
@@ -783,18 +786,30 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
     {
         const unsigned blocks = (unsigned)((N + 31) / 32);
         const int* hdr = reinterpret_cast<const int*>(pk);
-#define VQB_SPLIT(nch)                                                                                       \
-    do {                                                                                                     \
-        if (D == Dpad)                                                                                       \
-            split16_tokens_kernel<nch, true><<<blocks, 256, 0, s>>>(z, N, D, HW, hdr, z16, inv, znorm, zres);  \
-        else                                                                                                 \
-            split16_tokens_kernel<nch, false><<<blocks, 256, 0, s>>>(z, N, D, HW, hdr, z16, inv, znorm, zres); \
+#define VQB_SPLIT(nch)                                                                                                  \
+    do {                                                                                                                \
+        constexpr int kSm = (nch) * 32 * 33 * (int)sizeof(float);                                                       \
+        if (D == Dpad) {                                                                                                \
+            if (kSm > 48 * 1024)                                                                                        \
+                VQB_CUDA_TRY(cudaFuncSetAttribute(split16_tokens_kernel<nch, true>,                                     \
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));                   \
+            split16_tokens_kernel<nch, true><<<blocks, 256, kSm, s>>>(z, N, D, HW, hdr, z16, inv, znorm, zres);          \
+        } else {                                                                                                        \
+            if (kSm > 48 * 1024)                                                                                        \
+                VQB_CUDA_TRY(cudaFuncSetAttribute(split16_tokens_kernel<nch, false>,                                    \
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));                   \
+            split16_tokens_kernel<nch, false><<<blocks, 256, kSm, s>>>(z, N, D, HW, hdr, z16, inv, znorm, zres);         \
+        }                                                                                                               \
     } while (0)
         switch (Dpad / 32) {
             case 2: VQB_SPLIT(2); break;
             case 4: VQB_SPLIT(4); break;
             case 6: VQB_SPLIT(6); break;
-            default: VQB_SPLIT(8); break;
+            case 8: VQB_SPLIT(8); break;
+            case 10: VQB_SPLIT(10); break;
+            case 12: VQB_SPLIT(12); break;
+            case 14: VQB_SPLIT(14); break;
+            default: VQB_SPLIT(16); break;
         }
 #undef VQB_SPLIT
     }
@@ -824,28 +839,42 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
     p.pair_count = counts + 1;
     p.full_list = reinterpret_cast<int32_t*>(wsb + w.off_full);
     p.full_count = counts + 0;
+    p.acc_eps = D > 256 ? 1.f / 16384.f : 1.f / 32768.f;
     int rc;
     switch (Dpad / kTcBK) {
         case 1: rc = launch_tc16_t<1>(mz, me1, me2, me4, p, s); break;
         case 2: rc = launch_tc16_t<2>(mz, me1, me2, me4, p, s); break;
         case 3: rc = launch_tc16_t<3>(mz, me1, me2, me4, p, s); break;
         case 4: rc = launch_tc16_t<4>(mz, me1, me2, me4, p, s); break;
+        // 256 < D <= 512: the resident token tile takes 80-128 KB, 4-2 codebook stages remain; clusters of 2 only
+        case 5: rc = launch_tc16_cl<5, 2>(mz, me2, p, s); break;
+        case 6: rc = launch_tc16_cl<6, 2>(mz, me2, p, s); break;
+        case 7: rc = launch_tc16_cl<7, 2>(mz, me2, p, s); break;
+        case 8: rc = launch_tc16_cl<8, 2>(mz, me2, p, s); break;
         default:
-            set_error("fp16 tensor search supports 16 < D <= 256, got %d", D);
+            set_error("fp16 tensor search supports 16 < D <= %d, got %d", kTc16MaxD, D);
             return VQB_ERR_UNSUPPORTED;
     }
     if (rc != VQB_OK) return rc;
     // exact fp32 choice among the 4 (or 8) certified candidates of every token
     {
         const unsigned blocks = (unsigned)((N + 31) / 32);
-#define VQB_RESCORE(nch)                                                                                          \
-    do {                                                                                                          \
-        if (D == 32 * (nch))                                                                                      \
-            rescore_groups_kernel<nch, true><<<blocks, 256, 0, s>>>(z, E, p.half_norm, p.group1, p.group2, p.group3, N, \
-                                                                    D, HW, K, idx_out, dmin_out);                 \
-        else                                                                                                      \
-            rescore_groups_kernel<nch, false><<<blocks, 256, 0, s>>>(z, E, p.half_norm, p.group1, p.group2, p.group3, N, \
-                                                                     D, HW, K, idx_out, dmin_out);                \
+#define VQB_RESCORE(nch)                                                                                                \
+    do {                                                                                                                \
+        constexpr int kSm = (nch) * 32 * 36 * (int)sizeof(float);                                                       \
+        if (D == 32 * (nch)) {                                                                                          \
+            if (kSm > 48 * 1024)                                                                                        \
+                VQB_CUDA_TRY(cudaFuncSetAttribute(rescore_groups_kernel<nch, true>,                                     \
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));                   \
+            rescore_groups_kernel<nch, true><<<blocks, 256, kSm, s>>>(z, E, p.half_norm, p.group1, p.group2, p.group3, N, \
+                                                                      D, HW, K, idx_out, dmin_out);                     \
+        } else {                                                                                                        \
+            if (kSm > 48 * 1024)                                                                                        \
+                VQB_CUDA_TRY(cudaFuncSetAttribute(rescore_groups_kernel<nch, false>,                                    \
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));                   \
+            rescore_groups_kernel<nch, false><<<blocks, 256, kSm, s>>>(z, E, p.half_norm, p.group1, p.group2, p.group3,  \
+                                                                       N, D, HW, K, idx_out, dmin_out);                 \
+        }                                                                                                               \
     } while (0)
         switch ((D + 31) / 32) {
             case 1: VQB_RESCORE(1); break;
@@ -855,7 +884,15 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
             case 5: VQB_RESCORE(5); break;
             case 6: VQB_RESCORE(6); break;
             case 7: VQB_RESCORE(7); break;
-            default: VQB_RESCORE(8); break;
+            case 8: VQB_RESCORE(8); break;
+            case 9: VQB_RESCORE(9); break;
+            case 10: VQB_RESCORE(10); break;
+            case 11: VQB_RESCORE(11); break;
+            case 12: VQB_RESCORE(12); break;
+            case 13: VQB_RESCORE(13); break;
+            case 14: VQB_RESCORE(14); break;
+            case 15: VQB_RESCORE(15); break;
+            default: VQB_RESCORE(16); break;
         }
 #undef VQB_RESCORE
     }

@@ -37,7 +37,7 @@ def _search_kernels(D: int, algo: int, N: int = 0, K: int = 0, B: int = 0) -> in
     if algo == _cabi.ALGO_AUTO:
         algo = (_cabi.ALGO_DUAL_LOWD if (D == 4 and B >= 16 and N * K >= 1 << 30) else
                 (_cabi.ALGO_TCGEN05_TF32X3 if (D >= 5 and N * K >= 1 << 28) else _cabi.ALGO_LOWD_FMA) if D <= 16 else
-                _cabi.ALGO_TCGEN05_F16 if (16 < D <= 256 and (N == 0 or N * K * D >= 1 << 29))
+                _cabi.ALGO_TCGEN05_F16 if (16 < D <= 512 and (N == 0 or N * K * D >= 1 << 29))
                 else _cabi.ALGO_FP32_TILE)
     # lowd: search + stats; fp32: search (+ finalize) + stats; tcgen05: split, mma, re-score, finalize, stats
     # tf32x3: split, mma, chunk re-score, list search, stats
