@@ -12,7 +12,7 @@ rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 fails = 0
 t_start = time.time()
 for case in range(n_cases):
-    D = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 11, 16, 17, 31, 32, 40, 64, 65, 96, 128, 130, 192, 200, 256, 257, 300]))
+    D = int(rng.choice([1, 2, 3, 4, 4, 4, 5, 7, 8, 11, 16, 17, 31, 32, 40, 64, 65, 96, 128, 130, 192, 200, 256, 257, 300, 384, 512]))
     K = int(rng.choice([1, 2, 3, 31, 32, 33, 127, 128, 129, 255, 256, 257, 511, 1000, 2048, 4100, 9000]))
     B = int(rng.integers(1, 7))
     HW = int(rng.choice([1, 3, 4, 31, 32, 33, 100, 128, 256, 1000, 1024, 4096, 20000]))
@@ -31,8 +31,10 @@ for case in range(n_cases):
     algos = [0, 2]
     if D <= 16:
         algos += [1, 5]
-    if 16 < D <= 256:
+    if 16 < D <= 512:
         algos.append(4)
+    if D == 4 and B >= 2:
+        algos.append(6)
     if D % 64 == 0 and D <= 256:
         algos.append(3)
     res = {}
@@ -50,6 +52,9 @@ for case in range(n_cases):
         if not (worst < 2e-6) or int(idx.min()) < 0 or int(idx.max()) >= K:
             print(f"FAIL case {case} D={D} K={K} B={B} HW={HW} seed={seed} algo={a}: worst rel excess {worst:.3e}", flush=True)
             fails += 1
+    if 1 in res and 6 in res and not (torch.equal(res[1][0], res[6][0]) and torch.equal(res[1][1], res[6][1])):
+        print(f"FAIL case {case} D={D} K={K} B={B} HW={HW} seed={seed}: algo 6 != algo 1", flush=True)
+        fails += 1
     if 1 in res and 5 in res and not (torch.equal(res[1][0], res[5][0]) and torch.equal(res[1][1], res[5][1])):
         print(f"FAIL case {case} D={D} K={K} B={B} HW={HW} seed={seed}: algo 5 != algo 1", flush=True)
         fails += 1
