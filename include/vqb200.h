@@ -51,7 +51,7 @@ extern "C" {
 #define VQB_ALGO_TCGEN05_TF32X3 5 /* D <= 16: tf32x3 tcgen05 pass, certified 32-code chunk re-scored
                                      with the FMA chain of algo 1 (bit-identical indices) */
 
-#define VQB_ALGO_DUAL_LOWD 6 /* D == 4, >= 2 images: CUDA-core role and tf32x3 tensor role in ONE CTA on disjoint images
+#define VQB_ALGO_DUAL_LOWD 6 /* 3 <= D <= 16, >= 2 images: CUDA-core role and tf32x3 tensor role in ONE CTA on disjoint images
                                (different pipes of the SM); bit-identical indices to VQB_ALGO_LOWD_FMA */
 
 typedef void* vqb_stream_t; /* a cudaStream_t */

@@ -21,7 +21,7 @@ extern "C" {
 
 /*   "lowd_variant"       0..4   launch shape of the CUDA-core low-D search (0 = 256 threads x 2 CTA/SM)
  *   "lowd_ctas_per_sm"   0..3   0 = the variant's own residency; 1 leaves room for a co-running kernel
- *   "dual_permille"      1..999 share of the images handed to the tensor role of the two-engine search (algo 6)
+ *   "dual_permille"      0..999 share of the images handed to the tensor role of the two-engine search (algo 6; 0 = model)
  *   "tc16_cluster"       1|2|4  cluster size (codebook-stage multicast) of the fp16 tensor search
  *   "tclow_cluster"      1|2|4  same for the low-D tensor search
  *   "tclow_skip_stages"  0..7   bit mask: 1 tensor kernel, 2 chunk re-score, 4 exact list search (WRONG RESULTS)

@@ -27,7 +27,7 @@ def algos_for(D):
     out = [0, 2]
     if D <= 16:
         out += [1, 5]
-    if D == 4:
+    if 3 <= D <= 16:
         out.append(6)  # both engines in one CTA (needs >= 2 images; single-image cases are skipped below)
     if 16 < D <= 256:
         out.append(4)

@@ -57,6 +57,8 @@ def test_random_shape_all_kernels_agree(D, K, B, HW, seed):
     algos = [0]
     if D <= 16:
         algos += [1, 5]
+    if 3 <= D <= 16 and B >= 2:
+        algos.append(6)
     if 16 < D <= 512:
         algos.append(4)
     if D % 64 == 0 and D <= 256:
@@ -73,6 +75,8 @@ def test_random_shape_all_kernels_agree(D, K, B, HW, seed):
             assert float(((chosen - got64).abs() / scale)[differ].max()) < 1e-6
     if 1 in results:
         assert torch.equal(results[1][0], results[5][0]) and torch.equal(results[1][1], results[5][1])
+    if 6 in results:   # both engines in one CTA: bit-identical to the CUDA-core kernel
+        assert torch.equal(results[1][0], results[6][0]) and torch.equal(results[1][1], results[6][1])
     if 3 in results:
         assert torch.equal(results[3][0], results[4][0])
     if seed % 3 == 0 and K > 1:

@@ -99,7 +99,7 @@ extern "C" int vqb_tune(const char* key, int value) {
         set_lowd_variant(16 + value);
         return VQB_OK;
     }
-    if (strcmp(key, "dual_permille") == 0 && value >= 1 && value <= 999) {
+    if (strcmp(key, "dual_permille") == 0 && value >= 0 && value <= 999) {  // 0 = the built-in model
         set_dual_permille(value);
         return VQB_OK;
     }
@@ -176,9 +176,11 @@ static int resolve_algo(int algo, int D, int64_t N = 0, int K = 0, int64_t B = 0
     if (algo != VQB_ALGO_AUTO) return algo;
     if (D <= kLowDMax) {
         const bool large = (double)N * (double)K >= 268435456.0;  // 2^28 scores
-        // D = 4 (config C2) with enough images to split: both engines in one CTA, 2.32 ms against 2.94 (CUDA cores)
-        // and 2.82 (tensor cores) per 1M tokens x 16384 codes, identical results
-        if (dual_eligible(B, D) && B >= 16 && (double)N * (double)K >= 1073741824.0) return VQB_ALGO_DUAL_LOWD;
+        // enough images to split (D = 4 is config C2): both engines in one CTA, 2.32 ms against 2.94 (CUDA cores) and
+        // 2.82 (tensor cores) per 1M tokens x 16384 codes at D = 4, identical results
+        // (D <= 8 only: above that the 8-warp FMA role is too slow to be worth its share of the SM -- D = 12: 4.53 ms
+        // against 4.41 for the tensor kernel alone, profiles/r02_dual_dims.txt)
+        if (dual_eligible(B, D) && D <= 8 && B >= 16 && (double)N * (double)K >= 1073741824.0) return VQB_ALGO_DUAL_LOWD;
         return (D >= 5 && large) ? VQB_ALGO_TCGEN05_TF32X3 : VQB_ALGO_LOWD_FMA;
     }
     if (tc16_eligible_dim(D)) {
@@ -265,7 +267,8 @@ extern "C" int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, cons
                                        stats_out, s);
         case VQB_ALGO_DUAL_LOWD:
             if (!dual_eligible(B, D)) {
-                set_error("VQB_ALGO_DUAL_LOWD needs D == %d and at least 2 images, got D=%d B=%lld", kDualD, D, (long long)B);
+                set_error("VQB_ALGO_DUAL_LOWD needs %d <= D <= %d and at least 2 images, got D=%d B=%lld", kDualMinD, kLowDMax, D,
+                          (long long)B);
                 return VQB_ERR_UNSUPPORTED;
             }
             return launch_search_dual(z, B, D, HW, E, K, pack, idx_out, dmin_out, workspace, workspace_bytes, stats_out, s);

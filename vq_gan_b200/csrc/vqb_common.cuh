@@ -189,8 +189,9 @@ int launch_search_tclow(const float* z, int64_t B, int D, int64_t HW, const floa
                         const void* pack, int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes,
                         int64_t* stats_out, cudaStream_t s, bool share_sm = false);
 // two engines in one CTA (D = 4): CUDA-core role + tensor role on disjoint images (vqb_search_tclow.cu)
-constexpr int kDualD = 4;
-__host__ __device__ inline bool dual_eligible(int64_t B, int D) { return D == kDualD && B >= 2; }
+// D >= 3: below that the tensor role (whose cost does not drop with D) cannot keep up with the CUDA cores
+constexpr int kDualMinD = 3;
+__host__ __device__ inline bool dual_eligible(int64_t B, int D) { return D >= kDualMinD && D <= kLowDMax && B >= 2; }
 size_t search_dual_workspace_bytes(int64_t B, int D, int64_t HW, int K);
 int launch_search_dual(const float* z, int64_t B, int D, int64_t HW, const float* E, int K, const void* pack,
                        int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes, int64_t* stats_out, cudaStream_t s);

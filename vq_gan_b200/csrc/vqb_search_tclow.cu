@@ -664,21 +664,29 @@ int launch_search_tclow(const float* z, int64_t B, int D, int64_t HW, const floa
 // ---------------------------------------------------------------------------
 // two engines in one CTA: host side
 // ---------------------------------------------------------------------------
-// images handed to the tensor role.  Measured on B200 (scripts/dual_ab.py, 1M tokens x 16384 codes, D = 4): see the
-// sweep in profiles/; the default is the measured optimum.
-VQB_KNOB g_dual_permille = 500;
+// Share of the images handed to the tensor role: both roles should finish together.  Single-engine times per 1M tokens x
+// 16384 codes measured on B200 (profiles/r02_dim_sweep.txt): CUDA cores 0.735 ms x D; tensor cores 1.95 ms + 0.44 ms per
+// k-step of 8 tf32 slots ((3D+3)/8 of them).  D = 4: 0.51, measured optimum 0.50 (profiles/r02_dual_search_split_sweep.txt).
+VQB_KNOB g_dual_permille = 0;  // 0 = the model above; vqb_tune "dual_permille" overrides it
 #ifdef VQB_EXPERIMENTAL
 void set_dual_permille(int v) { g_dual_permille = v; }
 #endif
 
-static int64_t dual_tensor_images(int64_t B) {
-    int64_t bt = (B * g_dual_permille + 500) / 1000;
+static int64_t dual_tensor_images(int64_t B, int D) {
+    double share = g_dual_permille / 1000.0;
+    if (g_dual_permille <= 0) {
+        // (the FMA role has 8 warps here instead of the stand-alone kernel's 16: measured optimum 0.50 at D = 4 and 0.65
+        // at D = 8, profiles/r02_dual_dims.txt -> a correction linear in D)
+        const double t_fma = 0.735 * D * (0.96 + 0.0525 * (D - 4)), t_tc = 1.95 + 0.44 * tclow_steps(D);
+        share = t_fma / (t_fma + t_tc);
+    }
+    int64_t bt = (int64_t)((double)B * share + 0.5);
     return bt < 1 ? 1 : (bt > B - 1 ? B - 1 : bt);
 }
 
 size_t search_dual_workspace_bytes(int64_t B, int D, int64_t HW, int K) {
     if (!dual_eligible(B, D)) return 0;
-    return search_tclow_workspace_bytes(dual_tensor_images(B) * HW, D, K);
+    return search_tclow_workspace_bytes(dual_tensor_images(B, D) * HW, D, K);
 }
 
 __global__ void dual_stats_kernel(int64_t* stats, const int32_t* list_count, int64_t tensor_tokens) {
@@ -688,11 +696,13 @@ __global__ void dual_stats_kernel(int64_t* stats, const int32_t* list_count, int
     stats[3] = tensor_tokens;
 }
 
-int launch_search_dual(const float* z, int64_t B, int D, int64_t HW, const float* E, int K, const void* pack,
-                       int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes, int64_t* stats_out, cudaStream_t s) {
-    constexpr int DD = kDualD;
+template <int DD>
+static int launch_search_dual_d(const float* z, int64_t B, int64_t HW, const float* E, int K, const void* pack,
+                                int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes, int64_t* stats_out,
+                                cudaStream_t s) {
+    constexpr int D = DD;
     constexpr int CL = 2;
-    const int64_t Bt = dual_tensor_images(B);
+    const int64_t Bt = dual_tensor_images(B, D);
     const int64_t Nt = Bt * HW, Nf = (B - Bt) * HW;
     const LowWorkspace w = low_workspace(Nt, D);
     if (!ws || ws_bytes < w.total || (reinterpret_cast<uintptr_t>(ws) & 255u) != 0) {
@@ -727,13 +737,16 @@ int launch_search_dual(const float* z, int64_t B, int D, int64_t HW, const float
     p.list_count = count;
     p.share_sm = 1;
     const size_t tile_bytes = (size_t)p.steps * (kLowRows * 32);
-    int stages = kLowMaxStages;
+    const size_t fma_smem = round_up_z(LowDCfg<DD, 0>::kSmemBytes, 1024);
+    const size_t tc_fixed = 1024 + 512 + 2 * kLowRows * 4 * sizeof(float);
+    // codebook stages of the tensor role: what the FMA role's tiles leave of the 227 KB (8 at D = 4, 2 at D = 16)
+    int stages = (int)(((size_t)225 * 1024 - fma_smem - tc_fixed - 2 * tile_bytes) / tile_bytes);
+    stages = stages > kLowMaxStages ? kLowMaxStages : stages;
     const int n_n_tiles = p.Kpad / kLowBN;
     if (stages > n_n_tiles) stages = n_n_tiles;
     if (stages < 2) stages = 2;
     p.n_stages = stages;
-    const size_t fma_smem = round_up_z(LowDCfg<DD, 0>::kSmemBytes, 1024);
-    const size_t tc_smem = 1024 + (2 + (size_t)stages) * tile_bytes + 512 + 2 * kLowRows * 4 * sizeof(float);
+    const size_t tc_smem = tc_fixed + (2 + (size_t)stages) * tile_bytes;
     const size_t smem = fma_smem + tc_smem;
 
     DualFmaParams pf;
@@ -784,6 +797,21 @@ int launch_search_dual(const float* z, int64_t B, int D, int64_t HW, const float
         VQB_LAUNCH_CHECK("dual_stats_kernel");
     }
     return VQB_OK;
+}
+
+int launch_search_dual(const float* z, int64_t B, int D, int64_t HW, const float* E, int K, const void* pack,
+                       int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes, int64_t* stats_out, cudaStream_t s) {
+    switch (D) {
+#define VQB_CASE(d) \
+    case d:         \
+        return launch_search_dual_d<d>(z, B, HW, E, K, pack, idx_out, dmin_out, ws, ws_bytes, stats_out, s);
+        VQB_CASE(3) VQB_CASE(4) VQB_CASE(5) VQB_CASE(6) VQB_CASE(7) VQB_CASE(8) VQB_CASE(9) VQB_CASE(10)
+        VQB_CASE(11) VQB_CASE(12) VQB_CASE(13) VQB_CASE(14) VQB_CASE(15) VQB_CASE(16)
+#undef VQB_CASE
+        default:
+            set_error("two-engine search supports %d <= D <= %d, got %d", kDualMinD, kLowDMax, D);
+            return VQB_ERR_UNSUPPORTED;
+    }
 }
 
 }  // namespace vqb

@@ -35,7 +35,7 @@ def _count(kind: str, kernels: int = 0) -> None:
 def _search_kernels(D: int, algo: int, N: int = 0, K: int = 0, B: int = 0) -> int:
     """libvqb200 kernels one vqb_search_f32 call launches (mirrors resolve_algo in vqb_api.cu)."""
     if algo == _cabi.ALGO_AUTO:
-        algo = (_cabi.ALGO_DUAL_LOWD if (D == 4 and B >= 16 and N * K >= 1 << 30) else
+        algo = (_cabi.ALGO_DUAL_LOWD if (3 <= D <= 8 and B >= 16 and N * K >= 1 << 30) else
                 (_cabi.ALGO_TCGEN05_TF32X3 if (D >= 5 and N * K >= 1 << 28) else _cabi.ALGO_LOWD_FMA) if D <= 16 else
                 _cabi.ALGO_TCGEN05_F16 if (16 < D <= 512 and (N == 0 or N * K * D >= 1 << 29))
                 else _cabi.ALGO_FP32_TILE)
