@@ -1043,6 +1043,7 @@ def run_gpu_arm(args):
     c3_steps = max(3, min(args.steps, 20))
     c3 = measure_quantizer(args, "c3", world, rank, local_rank, device, peaks, fma, args.codebook, steps=c3_steps)
     variants = measure_codebook_variants(args, "c3", world, rank, device) if rank == 0 else None
+    variants_c2 = measure_codebook_variants(args, "c2", world, rank, device) if rank == 0 else None
     c5 = None
     if world > 1:
         B, D, H, W, K, desc = WORKLOADS["c5"]
@@ -1056,6 +1057,7 @@ def run_gpu_arm(args):
             c4 = {"workload": "c4full", "failed": f"{type(e).__name__}: {e}"[:300]} if rank == 0 else None
     if rank == 0:
         c3["codebooks"] = variants
+        line["codebooks"] = variants_c2
         line["c3"] = c3
         if c4 is not None:
             line["c4"] = c4

@@ -26,5 +26,8 @@ for k in ("c3", "c5"):
 if "c3" in d and d["c3"].get("codebooks"):
     for k, v in d["c3"]["codebooks"].items():
         print("   c3 codebook", k, v)
+if d.get("codebooks"):
+    for k, v in d["codebooks"].items():
+        print("   c2 codebook", k, v)
 if "c4" in d:
     print("== c4:", json.dumps(d["c4"])[:900])

@@ -35,6 +35,13 @@ __device__ __forceinline__ void key_unpack(unsigned long long key, float& d, int
     d = __int_as_float(bits);
 }
 
+// 4-byte asynchronous global -> shared copy; `valid` false writes a zero without touching `src`
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(src),
+                 "r"(valid ? 4 : 0)
+                 : "memory");
+}
+
 constexpr int kFtCompactCap = 4096;  // flagged tokens staged dim-major ([D][cap]) so every code split reads them coalesced
 
 // list mode pre-pass: zc[d][r] = z[token list[r]][d] for r < count (skipped when the list is longer than the buffer)
@@ -58,8 +65,9 @@ __global__ void __launch_bounds__(kFtThreads, 2)
                        const int32_t* __restrict__ list_count, int splits, int codes_per_split,
                        unsigned long long* __restrict__ keys, int64_t* __restrict__ idx_out,
                        float* __restrict__ dmin_out) {
-    __shared__ __align__(16) float As[kFtDk][kFtTokens + kFtPad];
-    __shared__ __align__(16) float Bs[kFtDk][kFtCodes + kFtPad];
+    // double buffered: cp.async fills buffer b^1 with k-step k+1 while k-step k is multiplied out of buffer b
+    __shared__ __align__(16) float As[2][kFtDk][kFtTokens + kFtPad];
+    __shared__ __align__(16) float Bs[2][kFtDk][kFtCodes + kFtPad];
     __shared__ int64_t tok_off[kFtTokens];
     __shared__ int64_t tok_id[kFtTokens];
 
@@ -114,31 +122,46 @@ __global__ void __launch_bounds__(kFtThreads, 2)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-            for (int k0 = 0; k0 < D; k0 += kFtDk) {
+            // software pipeline (cp.async, 4-byte copies with zero fill, no register staging): the unpipelined loop
+            // exposed one L2 round trip per 16 dimensions, which is what made the short token-list runs of the tensor
+            // paths latency-bound (175 us for ~400 tokens) and held the dense kernel at 34 TFLOP/s
+            constexpr int kRegA = (kFtDk * kFtTokens) / kFtThreads, kRegB = (kFtDk * kFtCodes) / kFtThreads;
+            const int a_mm = tid % kFtTokens, a_k = tid / kFtTokens;   // row of A is thread-constant (256 % 128 == 0)
+            const int64_t a_off = tok_off[a_mm];
+            const float* pa = zsrc + (a_off >= 0 ? a_off : 0) + (int64_t)a_k * zstride;
+            const int b_nn = tid / kFtDk, b_k = tid % kFtDk;
+            const float* pb = E + (size_t)(n0 + b_nn < K ? n0 + b_nn : 0) * D + b_k;
+            auto issue = [&](int buf, int k0) {
 #pragma unroll
-                for (int i = 0; i < (kFtDk * kFtTokens) / kFtThreads; ++i) {
-                    const int e = tid + i * kFtThreads;
-                    const int kk = e / kFtTokens, mm = e % kFtTokens;
-                    const int64_t off = tok_off[mm];
-                    float v = 0.f;
-                    if (off >= 0 && k0 + kk < D) v = __ldg(zsrc + off + (int64_t)(k0 + kk) * zstride);
-                    As[kk][mm] = v;
+                for (int i = 0; i < kRegA; ++i) {
+                    const int kk = a_k + i * (kFtThreads / kFtTokens);
+                    const bool ok = a_off >= 0 && k0 + kk < D;
+                    cp_async4(&As[buf][kk][a_mm], ok ? pa + (int64_t)(k0 + i * (kFtThreads / kFtTokens)) * zstride : zsrc, ok);
                 }
 #pragma unroll
-                for (int i = 0; i < (kFtDk * kFtCodes) / kFtThreads; ++i) {
-                    const int e = tid + i * kFtThreads;
-                    const int nn = e / kFtDk, kk = e % kFtDk;
-                    float v = 0.f;
-                    if (n0 + nn < K && k0 + kk < D) v = __ldg(E + (size_t)(n0 + nn) * D + k0 + kk);
-                    Bs[kk][nn] = v;
+                for (int i = 0; i < kRegB; ++i) {
+                    const int nn = b_nn + i * (kFtThreads / kFtDk);
+                    const bool ok = n0 + nn < K && k0 + b_k < D;
+                    cp_async4(&Bs[buf][b_k][nn], ok ? pb + (size_t)i * (kFtThreads / kFtDk) * D + k0 : E, ok);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            int buf = 0;
+            issue(0, 0);
+            for (int k0 = 0; k0 < D; k0 += kFtDk) {
+                if (k0 + kFtDk < D) {
+                    issue(buf ^ 1, k0 + kFtDk);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
                 }
                 __syncthreads();
 #pragma unroll
                 for (int kk = 0; kk < kFtDk; ++kk) {
-                    const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-                    const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
-                    const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-                    const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+                    const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+                    const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+                    const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+                    const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
                     const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
                     const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -146,7 +169,8 @@ __global__ void __launch_bounds__(kFtThreads, 2)
 #pragma unroll
                         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
                 }
-                __syncthreads();
+                __syncthreads();  // everyone is done with `buf` before the next iteration's copies overwrite it
+                buf ^= 1;
             }
             // epilogue: codes visited in increasing index order per thread
 #pragma unroll
