@@ -54,6 +54,10 @@ extern "C" {
 #define VQB_ALGO_DUAL_LOWD 6 /* 3 <= D <= 16, >= 2 images: CUDA-core role and tf32x3 tensor role in ONE CTA on disjoint images
                                (different pipes of the SM); bit-identical indices to VQB_ALGO_LOWD_FMA */
 
+/* flag OR-ed into `algo` = VQB_ALGO_TCGEN05_F16: the token split in `workspace` was already written by the producer of z
+ * (vqb_conv1x1_split_f32), skip the split pass */
+#define VQB_SEARCH_PRESPLIT 0x100
+
 typedef void* vqb_stream_t; /* a cudaStream_t */
 
 #if defined(__GNUC__)
@@ -169,6 +173,16 @@ VQB_API size_t vqb_conv1x1_workspace_bytes(int Cin, int Cout);
 VQB_API int vqb_conv1x1_f32(const float* x, int64_t B, int Cin, int64_t HW, const float* W,
                     const float* bias, int Cout, float* y, void* workspace, size_t workspace_bytes,
                     int algo, vqb_stream_t stream);
+
+/* pre_quant_conv fused with the quantizer's token split (vq_vae.py:115 feeding :118): y as vqb_conv1x1_f32 (tensor path
+ * only), plus -- while the accumulator is still in TMEM -- the fp16 token rows / scales / norms / rounding residuals the
+ * fp16 tensor search would otherwise compute from y (one read of y and one launch less).  `codebook_pack` is the prepared
+ * pack of the quantizer's codebook [K, Cout]; `search_workspace` (vqb_search_workspace_bytes(B, Cout, HW, K,
+ * VQB_ALGO_TCGEN05_F16) bytes) is then passed to vqb_search_f32 with algo = VQB_ALGO_TCGEN05_F16 | VQB_SEARCH_PRESPLIT. */
+VQB_API int vqb_conv1x1_split_f32(const float* x, int64_t B, int Cin, int64_t HW, const float* W,
+                          const float* bias, int Cout, float* y, void* workspace, size_t workspace_bytes,
+                          const void* codebook_pack, int K, void* search_workspace,
+                          size_t search_workspace_bytes, vqb_stream_t stream);
 
 /* ---- encoder tail / decoder tail normalisation + activation (next row N2) ---------------
  * `h = norm_out(h); h = F.silu(h)` (encoder_decoder.py:166-167 and 249-250; nn.GroupNorm(groups, C, eps, affine)):

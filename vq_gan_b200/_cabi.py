@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libvqb200.so")
 VQB_OK = 0
 ALGO_AUTO, ALGO_LOWD_FMA, ALGO_FP32_TILE, ALGO_TCGEN05, ALGO_TCGEN05_F16, ALGO_TCGEN05_TF32X3 = 0, 1, 2, 3, 4, 5
 ALGO_DUAL_LOWD = 6
+SEARCH_PRESPLIT = 0x100  # flag: the token split in the workspace was written by conv1x1_split
 ALGO_NAMES = {ALGO_AUTO: "auto", ALGO_LOWD_FMA: "lowd_fma", ALGO_FP32_TILE: "fp32_tile",
               ALGO_TCGEN05: "tcgen05", ALGO_TCGEN05_F16: "tcgen05_f16",
               ALGO_TCGEN05_TF32X3: "tcgen05_tf32x3", ALGO_DUAL_LOWD: "dual_lowd_fma+tf32x3"}
@@ -51,6 +52,8 @@ PROTOTYPES = {
     "vqb_conv1x1_workspace_bytes": (c_size_t, [c_int, c_int]),
     "vqb_conv1x1_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p,
                                 c_void_p, c_size_t, c_int, c_void_p]),
+    "vqb_conv1x1_split_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                      c_size_t, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "vqb_groupnorm_silu_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_float, c_void_p,
                                        c_void_p, c_void_p, c_void_p]),
     "vqb_groupnorm_silu_backward_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int,

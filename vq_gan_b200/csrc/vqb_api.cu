@@ -194,6 +194,7 @@ static int resolve_algo(int algo, int D, int64_t N = 0, int K = 0, int64_t B = 0
 
 extern "C" size_t vqb_search_workspace_bytes(int64_t B, int D, int64_t HW, int K, int algo) {
     if (B < 0 || HW < 0 || D <= 0 || K <= 0) return 0;
+    algo &= ~VQB_SEARCH_PRESPLIT;
     const int a = resolve_algo(algo, D, B * HW, K, B);
     if (a == VQB_ALGO_TCGEN05) return search_tc_workspace_bytes(B * HW, D, K);
     if (a == VQB_ALGO_TCGEN05_F16) return search_tc16_workspace_bytes(B * HW, D, K);
@@ -229,6 +230,12 @@ extern "C" int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, cons
         return VQB_ERR_INVALID_ARG;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bool presplit = (algo & VQB_SEARCH_PRESPLIT) != 0;
+    algo &= ~VQB_SEARCH_PRESPLIT;
+    if (presplit && algo != VQB_ALGO_TCGEN05_F16) {
+        set_error("VQB_SEARCH_PRESPLIT goes with VQB_ALGO_TCGEN05_F16 only (the split lives in that kernel's workspace)");
+        return VQB_ERR_INVALID_ARG;
+    }
     const int a = resolve_algo(algo, D, N, K, B);
     int rc;
     switch (a) {
@@ -257,7 +264,7 @@ extern "C" int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, cons
                 return VQB_ERR_UNSUPPORTED;
             }
             return launch_search_tc16(z, B, D, HW, E, K, pack, idx_out, dmin_out, workspace, workspace_bytes,
-                                      stats_out, s);
+                                      stats_out, s, presplit);
         case VQB_ALGO_TCGEN05_TF32X3:
             if (D > kLowDMax) {
                 set_error("VQB_ALGO_TCGEN05_TF32X3 needs D <= %d, got %d", kLowDMax, D);

@@ -207,7 +207,9 @@ void set_conv_debug(int v);
 size_t search_tc16_workspace_bytes(int64_t n_tokens, int D, int K);
 int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                        const void* pack, int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes,
-                       int64_t* stats_out, cudaStream_t s);
+                       int64_t* stats_out, cudaStream_t s, bool presplit = false);
+// where the token split lives inside a search workspace of search_tc16_workspace_bytes(N, D, K) bytes
+void tc16_split_pointers(void* ws, int64_t N, int D, __half** z16, float** inv_scale, float** znorm, float** zres);
 void set_lowd_variant(int v);
 void set_tc16_cluster(int c);
 

@@ -53,6 +53,14 @@ struct ConvParams {
     int64_t N, HW;
     int Cin, Cout;
     int dbg;  // experiments (vqb_tune "conv_debug"): 1 no activation loads, 2 no output stores, 4 one MMA in three
+    // fused token split for the fp16 tensor search that consumes y (vqb_conv1x1_split_f32; all null otherwise): what
+    // split16_tokens_kernel (vqb_search_tc16.cu) would compute from y, written while the accumulator is still in TMEM
+    __half* z16;          // [N][Dpad] token-major fp16(y * 2^e_i)
+    float* inv_scale;     // [N] 2^-(e_i + se)
+    float* znorm;         // [N] |y_i|
+    float* zres;          // [N] |y_i - fp16 image|
+    const int* header;    // codebook pack header (se = header[5])
+    int Dpad;
 };
 
 template <int CL>
@@ -252,23 +260,74 @@ __global__ void __launch_bounds__(kCvThreads, 1)
             }
             tc_mbar_wait(tm_full + acc, (round >> 1) & 1);
             tc_fence_after();
+            // Fused token split (p.z16 != null): ONE pass over the accumulator.  The per-token power-of-two scale is fixed
+            // from the first 32 channels (their largest magnitude times 8 lands in [512, 1024)): fp16 is a floating format, so
+            // the scale only has to keep the row inside the normal range; an outlier channel 512x larger than anything in
+            // the first chunk overflows to inf, the measured residual becomes NaN and the token takes the exact search --
+            // slower, never wrong.  (A first version scaled by the row maximum like split16_tokens_kernel, which needs a
+            // second TMEM pass: 0.98 -> 1.42 ms for 256 -> 256 channels, more than the 0.27 ms split pass it replaces.)
+            // No `if (ok)` inside the loop: it lets the compiler unswitch the loop on `ok`, which puts the .sync.aligned
+            // TMEM loads into divergent copies of the loop (observed: a hang whenever the last token tile is partial).
+            float sq = 0.f, res = 0.f, fwd = 1.f, back = 1.f;
+            int e = 0;
+            bool finite = true;
+            const bool stores = ok && !(p.dbg & 2);
+            __half* zp = p.z16 ? p.z16 + (size_t)(ok ? tok : 0) * p.Dpad : nullptr;
             for (int c0 = 0; c0 < p.Cout; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + lane_addr + acc * 256 + c0, r);
-                if (ok && !(p.dbg & 2)) {
-                    // Cout is a multiple of 16: two branch-free runs of 16 stores, bias from shared memory
-                    float* yp = p.y + yoff + (int64_t)c0 * p.HW;
+                float v[32];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (c0 + 16 * h < p.Cout) {
+                for (int j = 0; j < 32; ++j) v[j] = (c0 + j < p.Cout) ? __uint_as_float(r[j]) + bias_sm[c0 + j] : 0.f;
+                float* yp = p.y + yoff + (int64_t)c0 * p.HW;
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                *yp = __uint_as_float(r[16 * h + j]) + bias_sm[c0 + 16 * h + j];
-                                yp += p.HW;
-                            }
+                for (int j = 0; j < 32; ++j)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.global.f32 [%0], %1;\n\t}" ::"l"(yp + (int64_t)j * p.HW),
+                                 "f"(v[j]), "r"((int)(stores && c0 + j < p.Cout))
+                                 : "memory");
+                if (p.z16) {  // kernel-uniform
+                    if (c0 == 0) {
+                        float mx = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fabsf(v[j]));
+                        if (mx > 0.f && mx < INFINITY) {
+                            e = 6 - ilogbf(mx);  // first-chunk maximum -> [64, 128): 512x headroom to fp16's largest
+                            e = e < -100 ? -100 : (e > 100 ? 100 : e);
                         }
+                        fwd = __int_as_float((127 + e) << 23);
+                        back = __int_as_float((127 - e) << 23);
                     }
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float v0 = v[2 * j], v1 = v[2 * j + 1];
+                        sq = fmaf(v0, v0, sq);
+                        sq = fmaf(v1, v1, sq);
+                        finite &= (fabsf(v0) < INFINITY) && (fabsf(v1) < INFINITY);
+                        const __half h0 = __float2half_rn(v0 * fwd), h1 = __float2half_rn(v1 * fwd);
+                        const float d0 = v0 - __half2float(h0) * back, d1 = v1 - __half2float(h1) * back;
+                        res = fmaf(d0, d0, res);
+                        res = fmaf(d1, d1, res);
+                        packed[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                            "@p st.global.v4.b32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(zp + c0 + 8 * j),
+                            "r"(packed[4 * j]), "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3]),
+                            "r"((int)ok)
+                            : "memory");
                 }
+            }
+            if (p.z16 && ok) {
+                for (int c = (p.Cout + 31) / 32 * 32; c < p.Dpad; c += 8)  // zero columns up to the 64-channel block
+                    *reinterpret_cast<uint4*>(zp + c) = make_uint4(0u, 0u, 0u, 0u);
+                // a row that overflowed fp16 has res = inf/NaN: NaN scale -> every approximate score NaN -> exact search
+                const bool good = finite && res == res && res < INFINITY;
+                p.znorm[tok] = sqrtf(sq);
+                p.zres[tok] = good ? sqrtf(res) : 0.f;
+                p.inv_scale[tok] = good ? ldexpf(1.f, -(e + p.header[5])) : __int_as_float(0x7fc00000);
             }
             tc_fence_before();
             tc_mbar_arrive(tm_empty + acc);
@@ -359,9 +418,18 @@ extern "C" size_t vqb_conv1x1_workspace_bytes(int Cin, int Cout) {
     return conv_tc_eligible(Cin, Cout) ? 2 * round_up_z(sizeof(float) * (size_t)Cin * Cout, 1024) : 0;
 }
 
-extern "C" int vqb_conv1x1_f32(const float* x, int64_t B, int Cin, int64_t HW, const float* W, const float* bias,
-                               int Cout, float* y, void* workspace, size_t workspace_bytes, int algo,
-                               vqb_stream_t stream) {
+struct ConvSplitOut {
+    __half* z16 = nullptr;
+    float* inv_scale = nullptr;
+    float* znorm = nullptr;
+    float* zres = nullptr;
+    const int* header = nullptr;
+    int Dpad = 0;
+};
+
+static int conv1x1_impl(const float* x, int64_t B, int Cin, int64_t HW, const float* W, const float* bias, int Cout,
+                        float* y, void* workspace, size_t workspace_bytes, int algo, const ConvSplitOut& split,
+                        vqb_stream_t stream) {
     VQB_DEVICE_TRY();
     if (B < 0 || HW < 0 || Cin <= 0 || Cout <= 0) {
         set_error("vqb_conv1x1_f32: invalid shape B=%lld Cin=%d HW=%lld Cout=%d", (long long)B, Cin, (long long)HW, Cout);
@@ -375,6 +443,11 @@ extern "C" int vqb_conv1x1_f32(const float* x, int64_t B, int Cin, int64_t HW, c
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool tc = conv_tc_eligible(Cin, Cout) && algo != 2;
+    if (split.z16 && !tc) {
+        set_error("vqb_conv1x1_split_f32 needs the tensor path (Cin %% 32 == 0, Cout %% 16 == 0, Cout <= 256; Cin=%d Cout=%d)", Cin,
+                  Cout);
+        return VQB_ERR_UNSUPPORTED;
+    }
     if (algo == 1 && !tc) {
         set_error("vqb_conv1x1_f32: the tensor path needs Cin %% 32 == 0 and Cout %% 16 == 0, Cout <= 256 (Cin=%d Cout=%d)", Cin, Cout);
         return VQB_ERR_UNSUPPORTED;
@@ -412,6 +485,12 @@ extern "C" int vqb_conv1x1_f32(const float* x, int64_t B, int Cin, int64_t HW, c
     p.Cin = Cin;
     p.Cout = Cout;
     p.dbg = g_conv_debug;
+    p.z16 = split.z16;
+    p.inv_scale = split.inv_scale;
+    p.znorm = split.znorm;
+    p.zres = split.zres;
+    p.header = split.header;
+    p.Dpad = split.Dpad;
     const size_t stage_bytes = 2 * (size_t)kCvABytes + 2 * (size_t)Cout * kCvKB * 4;
     const size_t smem = 1024 + kCvStages * stage_bytes + 256 + 1024;
     const int n_tiles = (int)((N + kCvTok - 1) / kCvTok);
@@ -443,4 +522,34 @@ extern "C" int vqb_conv1x1_f32(const float* x, int64_t B, int Cin, int64_t HW, c
         VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv1x1_tc_kernel<1>, mhi, mlo, p));
     }
     return VQB_OK;
+}
+
+extern "C" int vqb_conv1x1_f32(const float* x, int64_t B, int Cin, int64_t HW, const float* W, const float* bias,
+                               int Cout, float* y, void* workspace, size_t workspace_bytes, int algo,
+                               vqb_stream_t stream) {
+    return conv1x1_impl(x, B, Cin, HW, W, bias, Cout, y, workspace, workspace_bytes, algo, ConvSplitOut(), stream);
+}
+
+// pre_quant_conv fused with the quantizer's token split (vq_vae.py:115 feeding :118): y as above, plus -- while the
+// accumulator is still in TMEM -- the fp16 token rows, scales, norms and rounding residuals that the fp16 tensor search
+// would otherwise compute from y with split16_tokens_kernel (one read of y and a launch less).  `search_workspace` is the
+// workspace the following vqb_search_f32(..., algo = VQB_ALGO_TCGEN05_F16 | VQB_SEARCH_PRESPLIT) call will be given.
+extern "C" int vqb_conv1x1_split_f32(const float* x, int64_t B, int Cin, int64_t HW, const float* W, const float* bias,
+                                     int Cout, float* y, void* workspace, size_t workspace_bytes, const void* codebook_pack,
+                                     int K, void* search_workspace, size_t search_workspace_bytes, vqb_stream_t stream) {
+    if (!codebook_pack || !search_workspace || K <= 0 || !tc16_eligible_dim(Cout)) {
+        set_error("vqb_conv1x1_split_f32: needs a codebook pack, a search workspace and 16 < Cout <= %d", kTc16MaxD);
+        return VQB_ERR_INVALID_ARG;
+    }
+    const int64_t N = B * HW;
+    if (search_workspace_bytes < search_tc16_workspace_bytes(N, Cout, K) ||
+        (reinterpret_cast<uintptr_t>(search_workspace) & 255u) != 0) {
+        set_error("vqb_conv1x1_split_f32: search workspace too small or misaligned");
+        return VQB_ERR_WORKSPACE;
+    }
+    ConvSplitOut so;
+    tc16_split_pointers(search_workspace, N, Cout, &so.z16, &so.inv_scale, &so.znorm, &so.zres);
+    so.header = reinterpret_cast<const int*>(codebook_pack);
+    so.Dpad = tc16_dpad(Cout);
+    return conv1x1_impl(x, B, Cin, HW, W, bias, Cout, y, workspace, workspace_bytes, 1, so, stream);
 }

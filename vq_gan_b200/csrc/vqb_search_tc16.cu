@@ -696,6 +696,15 @@ static T16Workspace t16_workspace(int64_t N, int D) {
     return w;
 }
 
+void tc16_split_pointers(void* ws, int64_t N, int D, __half** z16, float** inv_scale, float** znorm, float** zres) {
+    const T16Workspace w = t16_workspace(N, D);
+    unsigned char* b = static_cast<unsigned char*>(ws);
+    *z16 = reinterpret_cast<__half*>(b + w.off_z16);
+    *inv_scale = reinterpret_cast<float*>(b + w.off_inv);
+    *znorm = reinterpret_cast<float*>(b + w.off_znorm);
+    *zres = reinterpret_cast<float*>(b + w.off_zres);
+}
+
 size_t search_tc16_workspace_bytes(int64_t n_tokens, int D, int K) {
     (void)K;
     return t16_workspace(n_tokens, D).total;
@@ -761,7 +770,7 @@ static int launch_tc16_t(const CUtensorMap& mz, const CUtensorMap& me1, const CU
 
 int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float* E, int K, const void* pack,
                        int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes, int64_t* stats_out,
-                       cudaStream_t s) {
+                       cudaStream_t s, bool presplit) {
     const int64_t N = B * HW;
     const T16Workspace w = t16_workspace(N, D);
     if (!ws || ws_bytes < w.total) {
@@ -783,7 +792,7 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
 
     VQB_CUDA_TRY(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), s));
     const int Dpad = L.Dpad;
-    {
+    if (!presplit) {  // (presplit: the producer of z -- vqb_conv1x1_split_f32 -- already filled z16 / inv / znorm / zres)
         const unsigned blocks = (unsigned)((N + 31) / 32);
         const int* hdr = reinterpret_cast<const int*>(pk);
 #define VQB_SPLIT(nch)                                                                                                  \

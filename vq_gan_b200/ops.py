@@ -104,7 +104,8 @@ def prepare_codebook(weight: Tensor) -> Tensor:
         return _prepare(weight.contiguous())
 
 
-def _search_into(z: Tensor, weight: Tensor, algo: int, want_dmin: bool, pack: Optional[Tensor] = None):
+def _search_into(z: Tensor, weight: Tensor, algo: int, want_dmin: bool, pack: Optional[Tensor] = None,
+                 split_ws: Optional[Tensor] = None):
     B, D, HW, K = _shape_bdhw(z, weight)
     dev = z.device
     if pack is None:
@@ -114,15 +115,25 @@ def _search_into(z: Tensor, weight: Tensor, algo: int, want_dmin: bool, pack: Op
     idx = torch.empty((B,) + tuple(z.shape[2:]), dtype=torch.int64, device=dev)
     dmin = torch.empty(idx.shape, dtype=torch.float32, device=dev) if want_dmin else None
     stats = torch.empty(4, dtype=torch.int64, device=dev)  # every search path writes all four entries
-    ws_bytes = lib().vqb_search_workspace_bytes(B, D, HW, K, algo)
-    ws = _bytes(ws_bytes, dev)
+    if split_ws is not None:
+        # the producer of z (conv1x1_split) already wrote the token split into this workspace
+        if pack is None:
+            raise RuntimeError("search: a pre-split workspace needs the codebook pack it was built against")
+        algo = _cabi.ALGO_TCGEN05_F16 | _cabi.SEARCH_PRESPLIT
+        ws_bytes = lib().vqb_search_workspace_bytes(B, D, HW, K, _cabi.ALGO_TCGEN05_F16)
+        if split_ws.device != dev or split_ws.dtype != torch.uint8 or split_ws.numel() < ws_bytes:
+            raise RuntimeError("search: the pre-split workspace does not fit this problem")
+        ws = split_ws
+    else:
+        ws_bytes = lib().vqb_search_workspace_bytes(B, D, HW, K, algo)
+        ws = _bytes(ws_bytes, dev)
     prof = PROFILE
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     check(lib().vqb_search_f32(_p(z), B, D, HW, _p(weight), K, _p(pack), _p(idx), _p(dmin), _p(ws),
                                ws_bytes, algo, _p(stats), _stream()), "vqb_search_f32")
-    _count("search", _search_kernels(D, algo, B * HW, K, B))
+    _count("search", _search_kernels(D, algo & 0xff, B * HW, K, B) - (1 if split_ws is not None else 0))
     if prof is not None:
         ev1.record()
         prof.append((ev0, ev1))
@@ -162,8 +173,8 @@ def _(z, weight, algo=0, pack=None):
 # full forward (quantizer.py:63-101)
 # ---------------------------------------------------------------------------
 @torch.library.custom_op("vqb200::quantize", mutates_args=())
-def quantize(z: Tensor, weight: Tensor, beta: float, algo: int = 0
-             ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+def quantize(z: Tensor, weight: Tensor, beta: float, algo: int = 0, pack: Optional[Tensor] = None,
+             split_ws: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """(z_q, vq_loss, mse, indices, stats).  z_q is the straight-through VALUE
     z + (e - z); vq_loss = mse + beta*mse; mse is the value of both
     codebook_loss and commitment_loss."""
@@ -178,7 +189,7 @@ def quantize(z: Tensor, weight: Tensor, beta: float, algo: int = 0
                 torch.empty((B,) + tuple(z.shape[2:]), dtype=torch.int64, device=z.device),
                 torch.zeros(4, dtype=torch.int64, device=z.device))
     with _on(z.device):
-        idx, _, stats = _search_into(z, weight, algo, False)
+        idx, _, stats = _search_into(z, weight, algo, False, pack, split_ws)
         z_q = torch.empty_like(z)
         loss = torch.empty(2, dtype=torch.float32, device=z.device)
         pbytes = lib().vqb_tail_partials_bytes(B * HW)
@@ -198,7 +209,7 @@ def quantize(z: Tensor, weight: Tensor, beta: float, algo: int = 0
 
 
 @quantize.register_fake
-def _(z, weight, beta, algo=0):
+def _(z, weight, beta, algo=0, pack=None, split_ws=None):
     shape = (z.shape[0],) + tuple(z.shape[2:])
     return (torch.empty_like(z), z.new_empty(()), z.new_empty(()),
             z.new_empty(shape, dtype=torch.int64), z.new_empty((4,), dtype=torch.int64))
@@ -243,7 +254,7 @@ def _(z, weight, indices, g_zq, g_vq, beta, need_dE):
 
 
 def _quantize_setup(ctx, inputs, output):
-    z, weight, beta, _algo = inputs
+    z, weight, beta = inputs[0], inputs[1], inputs[2]
     ctx.save_for_backward(z, weight, output[3])
     ctx.beta = beta
     # only z_q and vq_loss carry gradient.  `mse` is the LOGGED value of codebook_loss / commitment_loss (the
@@ -256,7 +267,7 @@ def _quantize_bwd(ctx, g_zq, g_vq, g_mse, g_idx, g_stats):
     z, weight, idx = ctx.saved_tensors
     need_dz, need_dE = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
     dz, dE = quantize_backward(z, weight, idx, g_zq, g_vq, ctx.beta, bool(need_dE))
-    return (dz if need_dz else None), (dE if need_dE else None), None, None
+    return (dz if need_dz else None), (dE if need_dE else None), None, None, None, None
 
 
 torch.library.register_autograd("vqb200::quantize", _quantize_bwd, setup_context=_quantize_setup)
@@ -515,6 +526,72 @@ def _(x, weight, bias, algo=0):
     return x.new_empty((x.shape[0], weight.shape[0]) + tuple(x.shape[2:]))
 
 
+def split_eligible(cin: int, cout: int, tokens: int, K: int) -> bool:
+    """Shapes for which `QuantConv1x1.feed` switches to `conv1x1_split`: the convolution's tensor path, feeding a
+    quantizer whose automatic choice is the fp16 tensor search (the consumer of the split), and Cout <= 128 -- measured
+    (scripts/conv_split_bench.py): 128 -> 64 channels 5.27 -> 4.64 ms for conv + quantizer forward on 1M tokens, but at
+    256 -> 256 the extra epilogue work of the tensor-bound convolution (+0.32 ms) outweighs the split pass it replaces
+    (0.27 ms).  The op itself accepts Cout up to 256."""
+    return (cin % 32 == 0 and cout % 16 == 0 and 16 < cout <= 128 and tokens * K * cout >= (1 << 29))
+
+
+@torch.library.custom_op("vqb200::conv1x1_split", mutates_args=())
+def conv1x1_split(x: Tensor, weight: Tensor, bias: Optional[Tensor], codebook: Tensor, pack: Tensor) -> Tuple[Tensor, Tensor]:
+    """(y, search_workspace): the 1x1 convolution of `conv1x1` (tensor path) that ALSO writes, from the accumulator, the
+    token split the fp16 tensor search of the quantizer with `codebook` [K, Cout] needs (`pack` = prepare_codebook(codebook)).
+    Hand both to `quantize(y, codebook, beta, 0, pack, search_workspace)`: the search then skips its own split pass."""
+    _need_cuda_f32(x, "x")
+    _need_cuda_f32(weight, "weight")
+    _need_cuda_f32(codebook, "codebook")
+    x = x.contiguous()
+    weight = weight.reshape(weight.shape[0], -1).contiguous()
+    if bias is not None:
+        _need_cuda_f32(bias, "bias")
+        bias = bias.contiguous()
+    B, Cin, Cout = int(x.shape[0]), int(x.shape[1]), int(weight.shape[0])
+    K = int(codebook.shape[0])
+    if int(weight.shape[1]) != Cin or int(codebook.shape[1]) != Cout:
+        raise RuntimeError("conv1x1_split: channel mismatch between x, the weight and the codebook")
+    HW = x.numel() // max(B * Cin, 1)
+    y = torch.empty((B, Cout) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    with _on(x.device):
+        sb = lib().vqb_search_workspace_bytes(B, Cout, HW, K, _cabi.ALGO_TCGEN05_F16)
+        sws = _bytes(sb, x.device)
+        if y.numel() == 0:
+            return y, sws
+        wb = lib().vqb_conv1x1_workspace_bytes(Cin, Cout)
+        ws = _bytes(wb, x.device)
+        prof = PROFILE_CONV
+        if prof is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        check(lib().vqb_conv1x1_split_f32(_p(x), B, Cin, HW, _p(weight), _p(bias), Cout, _p(y), _p(ws), wb, _p(pack), K,
+                                          _p(sws), sb, _stream()), "vqb_conv1x1_split_f32")
+        if prof is not None:
+            ev1.record()
+            prof.append((ev0, ev1))
+        _count("conv", 2)
+    return y, sws
+
+
+@conv1x1_split.register_fake
+def _(x, weight, bias, codebook, pack):
+    return (x.new_empty((x.shape[0], weight.shape[0]) + tuple(x.shape[2:])), x.new_empty((1,), dtype=torch.uint8))
+
+
+def _conv1x1_split_setup(ctx, inputs, output):
+    x, weight, bias, _codebook, _pack = inputs
+    ctx.save_for_backward(x, weight)
+    ctx.has_bias = bias is not None
+    ctx.algo = 0
+    ctx.mark_non_differentiable(output[1])
+
+
+def _conv1x1_split_bwd(ctx, gy, g_ws):
+    gx, gw, gb, _ = _conv1x1_bwd(ctx, gy)
+    return gx, gw, gb, None, None
+
+
 def _conv1x1_setup(ctx, inputs, output):
     x, weight, bias, algo = inputs
     ctx.save_for_backward(x, weight)
@@ -543,6 +620,7 @@ def _conv1x1_bwd(ctx, gy):
 
 
 torch.library.register_autograd("vqb200::conv1x1", _conv1x1_bwd, setup_context=_conv1x1_setup)
+torch.library.register_autograd("vqb200::conv1x1_split", _conv1x1_split_bwd, setup_context=_conv1x1_split_setup)
 
 
 # ---------------------------------------------------------------------------

@@ -145,8 +145,16 @@ class VectorQuantizer(nn.Module):
                 f"z has {z.shape[1]} channels but embedding_dim is {self.embedding_dim}")
         if z.dtype != torch.float32:
             z = z.float()
+        pack = split_ws = None
+        pre = getattr(z, "_vqb_presplit", None)
+        if pre is not None:
+            # z comes from a QuantConv1x1 that feeds this quantizer: the convolution already wrote the token split of the
+            # fp16 tensor search into a workspace (valid only for exactly this tensor and this codebook version)
+            w = self.embedding.weight
+            if pre[2] == (w.data_ptr(), w._version, tuple(z.shape)) and z.is_contiguous() and self.algo in (0, 4):
+                split_ws, pack = pre[0], pre[1]
         z_q, vq_loss, mse, indices, stats = ops.quantize(z, self.embedding.weight,
-                                                         float(self.commitment_cost), self.algo)
+                                                         float(self.commitment_cost), self.algo, pack, split_ws)
         self.last_search_stats = stats
         self.last_mse = mse.detach()  # device copy of the logged loss (multi-GPU statistics need no host round trip)
         if self.return_format == "taming":
@@ -218,12 +226,31 @@ class QuantConv1x1(nn.Conv2d):
                              f"(got {kernel_size}, {stride}, {padding})")
         super().__init__(in_channels, out_channels, kernel_size=1, bias=bool(bias))
         self.algo = algo
+        self._feeds = None
+
+    def feed(self, quantizer: "VectorQuantizer") -> "QuantConv1x1":
+        """Declares that this layer is the `pre_quant_conv` in front of `quantizer` (vq_vae.py:115 -> :118).  When the
+        shapes qualify (`ops.split_eligible`) the forward then runs `vqb_conv1x1_split_f32`: the convolution's epilogue
+        also emits the fp16 token rows / scales / norms the quantizer's tensor search needs, straight from the TMEM
+        accumulator, and the search skips its own pass over z.  Results are unchanged."""
+        import weakref
+        self._feeds = weakref.ref(quantizer)
+        return self
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if x.dim() != 4:
             raise RuntimeError(f"expected x of shape [B, C, H, W], got {tuple(x.shape)}")
         if x.dtype != torch.float32:
             x = x.float()
+        vq = self._feeds() if self._feeds is not None else None
+        if vq is not None and x.is_cuda and self.algo in (0, 1) and vq.algo in (0, 4) and vq.embedding_dim == self.out_channels:
+            tokens = x.numel() // max(int(x.shape[1]), 1)
+            if ops.split_eligible(self.in_channels, self.out_channels, tokens, vq.num_embeddings):
+                w = vq.embedding.weight
+                pack = ops.prepare_codebook(w.detach())
+                y, sws = ops.conv1x1_split(x, self.weight, self.bias, w.detach(), pack)
+                y._vqb_presplit = (sws, pack, (w.data_ptr(), w._version, tuple(y.shape)))
+                return y
         return ops.conv1x1(x, self.weight, self.bias, self.algo)
 
 
