@@ -990,8 +990,9 @@ def measure_codebook_variants(args, workload, world, rank, device, kinds=("refin
         b.synchronize()
         st = st.tolist()
         out[kind] = {"search_ms": a.elapsed_time(b) / n, "algo": int(st[1]), "exact_full_search_tokens": int(st[0]),
-                     "multi_group_tokens": int(st[2]), "filtered_exact_tokens": int(st[3]),
-                     "codes_used": int(torch.unique(idx).numel())}
+                     "multi_group_tokens": int(st[2]), "codes_used": int(torch.unique(idx).numel())}
+        if int(st[1]) == 6:
+            out[kind]["tensor_role_tokens"] = int(st[3])
         del E, idx, dmin
     del z
     torch.cuda.empty_cache()
