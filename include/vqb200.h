@@ -184,6 +184,16 @@ VQB_API int vqb_conv1x1_split_f32(const float* x, int64_t B, int Cin, int64_t HW
                           const void* codebook_pack, int K, void* search_workspace,
                           size_t search_workspace_bytes, vqb_stream_t stream);
 
+/* parameter gradients of the same layer (autograd of vq_vae.py:115,121): a reduction over the tokens,
+ *   dW_accum[Cout, Cin] += sum_{b,hw} dy[b, o, hw] * x[b, c, hw]      dbias_accum[Cout] += sum_{b,hw} dy[b, o, hw]
+ * 3xTF32 tcgen05 (fp32-level accuracy), both operands straight from NCHW by TMA.  Both outputs are ACCUMULATED into
+ * (the caller zeroes them; dbias_accum nullable).  Shapes: vqb_conv1x1_dw_supported(Cin, Cout, HW) != 0, i.e.
+ * Cin % 16 == 0, Cout <= 256, HW >= 32, HW % 4 == 0; anything else returns VQB_ERR_UNSUPPORTED (no slow path: the
+ * caller keeps its library GEMM for such shapes). */
+VQB_API int vqb_conv1x1_dw_supported(int Cin, int Cout, int64_t HW);
+VQB_API int vqb_conv1x1_dw_f32(const float* dy, const float* x, int64_t B, int Cin, int Cout, int64_t HW,
+                       float* dW_accum, float* dbias_accum, vqb_stream_t stream);
+
 /* ---- encoder tail / decoder tail normalisation + activation (next row N2) ---------------
  * `h = norm_out(h); h = F.silu(h)` (encoder_decoder.py:166-167 and 249-250; nn.GroupNorm(groups, C, eps, affine)):
  *   y[b,c,hw] = silu((x - mean[b,g]) * rstd[b,g] * gamma[c] + beta[c]),  g = c / (C / groups)

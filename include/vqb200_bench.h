@@ -23,6 +23,9 @@ extern "C" {
  *   "lowd_ctas_per_sm"   0..3   0 = the variant's own residency; 1 leaves room for a co-running kernel
  *   "dual_permille"      0..999 share of the images handed to the tensor role of the two-engine search (algo 6; 0 = model)
  *   "tc16_cluster"       1|2|4  cluster size (codebook-stage multicast) of the fp16 tensor search
+ *   "tc16_group"         0|4|8  codes per candidate group of the fp16 tensor search (0 = 8 up to padded D 128, 4 above)
+ *   "norm_cluster"       0|1|2  GroupNorm+SiLU: round-1 staged kernels only / product (default 1) / also clusters of
+ *                               2-8 CTAs per (image, group) (measured slower)
  *   "tclow_cluster"      1|2|4  same for the low-D tensor search
  *   "tclow_skip_stages"  0..7   bit mask: 1 tensor kernel, 2 chunk re-score, 4 exact list search (WRONG RESULTS)
  *   "fwd_pass_channels" / "bwd_pass_channels"  64|128|192|256  channels per pass of the tiled tail kernels

@@ -1,10 +1,12 @@
 """GroupNorm + SiLU (row N2): fused kernel vs stock torch, forward and backward, encoder-tail and decoder-tail shapes."""
 import os
+os.environ.setdefault("VQB200_EXPERIMENTAL", "1")
 import sys
 import torch
 import torch.nn.functional as F
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from vq_gan_b200 import ops
+from vq_gan_b200 import _cabi, ops
+lib = _cabi.lib()
 PEAK = 6530.0
 
 
@@ -21,7 +23,9 @@ def timed(fn, n=10):
     return a.elapsed_time(b) / n
 
 
-for B, C, H, W in ((64, 512, 32, 32), (1024, 512, 32, 32), (16, 128, 256, 256)):
+for B, C, H, W, mode in [(b, c, h, w, m) for (b, c, h, w) in ((64, 512, 32, 32), (1024, 512, 32, 32), (256, 512, 16, 16),
+                                                             (16, 128, 256, 256)) for m in (0, 1)]:
+    _cabi.check(lib.vqb_tune(b"norm_cluster", mode), "t")
     x = torch.randn(B, C, H, W, device="cuda")
     w = torch.randn(C, device="cuda")
     b = torch.randn(C, device="cuda")
@@ -37,5 +41,5 @@ for B, C, H, W in ((64, 512, 32, 32), (1024, 512, 32, 32), (16, 128, 256, 256)):
         xr.grad = None
         F.silu(F.group_norm(xr, 32, w, b, 1e-6)).backward(gy)
     ttb = timed(torch_fb)
-    print(f"[{B},{C},{H},{W}] fwd fused {tf:.3f} ms ({2 * nbytes / tf / 1e6 / PEAK:.2f} of HBM peak for 2 passes) vs torch {tt:.3f} ms; "
+    print(f"[{B},{C},{H},{W}] cluster={mode} fwd fused {tf:.3f} ms ({2 * nbytes / tf / 1e6 / PEAK:.2f} of HBM peak for 2 passes) vs torch {tt:.3f} ms; "
           f"bwd fused {tb:.3f} ms ({3 * nbytes / tb / 1e6 / PEAK:.2f} for 3 passes); torch fwd+bwd {ttb:.3f} ms", flush=True)

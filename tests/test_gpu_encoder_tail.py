@@ -16,7 +16,12 @@ def _ref(x, gn):
 @pytest.mark.parametrize("B,C,H,W,G", [(4, 512, 32, 32, 32),     # encoder tail (staged in shared memory)
                                         (2, 128, 256, 256, 32),   # decoder tail (1 MB per group: global passes)
                                         (3, 48, 7, 9, 8),         # ragged: HW % 4 != 0
-                                        (1, 64, 16, 16, 64)])     # one channel per group
+                                        (1, 64, 16, 16, 64),      # one channel per group
+                                        (2, 64, 64, 64, 16),      # cluster of 4 / 2 CTAs per group, 4 segments per channel
+                                        (2, 64, 64, 64, 8),       # cluster of 8 / 4
+                                        (3, 6, 50, 50, 2),        # a channel split between two CTAs of a cluster
+                                        (2, 12, 35, 35, 2),       # cluster of 2 with HW % 4 != 0 (scalar path)
+                                        (5, 512, 16, 16, 32)])    # 16 x 16 latents (f = 16 encoders)
 def test_groupnorm_silu_matches_torch(B, C, H, W, G):
     from vq_gan_b200 import GroupNormSiLU
     torch.manual_seed(C + H)

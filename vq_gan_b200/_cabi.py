@@ -54,6 +54,8 @@ PROTOTYPES = {
                                 c_void_p, c_size_t, c_int, c_void_p]),
     "vqb_conv1x1_split_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                       c_size_t, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "vqb_conv1x1_dw_supported": (c_int, [c_int, c_int, c_int64]),
+    "vqb_conv1x1_dw_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "vqb_groupnorm_silu_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int, c_float, c_void_p,
                                        c_void_p, c_void_p, c_void_p]),
     "vqb_groupnorm_silu_backward_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_int,

@@ -107,6 +107,14 @@ extern "C" int vqb_tune(const char* key, int value) {
         set_tc16_cluster(16 + value);
         return VQB_OK;
     }
+    if (strcmp(key, "norm_cluster") == 0 && value >= 0 && value <= 2) {
+        set_norm_cluster(value);
+        return VQB_OK;
+    }
+    if (strcmp(key, "tc16_group") == 0 && (value == 0 || value == 4 || value == 8)) {
+        set_tc16_cluster(32 + value);
+        return VQB_OK;
+    }
     if (strcmp(key, "tc16_cluster") == 0 && (value == 1 || value == 2 || value == 4)) {
         set_tc16_cluster(value);
         return VQB_OK;

@@ -78,6 +78,7 @@ __host__ __device__ inline bool tc_eligible_dim(int D) {  // bf16x3 kernel: whol
     return D >= kTcMinD && D <= kTcMaxD && (D % 64) == 0;
 }
 // single-pass fp16 kernel: any 16 < D <= 256, the fp16 operand images are zero-padded to 64-channel blocks
+constexpr int kTc16WideGroupDpad = 64;   // fp16 kernel: candidate groups of 8 codes up to this padded D, of 4 above
 __host__ __device__ inline bool tc16_eligible_dim(int D) { return D > kLowDMax && D <= kTc16MaxD; }
 __host__ __device__ inline int tc16_dpad(int D) { return round_up_i(D, 64); }
 
@@ -212,5 +213,6 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
 void tc16_split_pointers(void* ws, int64_t N, int D, __half** z16, float** inv_scale, float** znorm, float** zres);
 void set_lowd_variant(int v);
 void set_tc16_cluster(int c);
+void set_norm_cluster(int v);
 
 }  // namespace vqb

@@ -188,7 +188,14 @@ __device__ __forceinline__ void top4_insert(Top4& g, float v, int i) {
 // kernel: 32 KB of B per 512 tensor cycles per SM) drops by CL.
 // BR: the sorted insert runs only when the group key beats the current fourth-best (a warp-divergent branch taken by
 // ~14 % of the warp-steps: the probability that group n of a token enters its top-4 is 4/n) instead of unconditionally
-template <int NKB, int CL, bool BR = false>
+// GS: codes per candidate group (4 or 8).  The epilogue costs 4 FFMA + (GS/2 + 8) ALU-pipe operations per group, i.e.
+// 2.5 ALU operations per score with groups of 4 and 1.5 with groups of 8; the price of wider groups is a re-score
+// over 8 / 16 / 24 exact candidates instead of 4 / 8 / 12.  Measured (scripts/tc16_group_ab.py, 1 M tokens x 16 384
+// codes, whole search): D = 32 4.19 -> 3.56 ms, D = 64 4.23 -> 3.66 ms, D = 128 4.8 -> 4.6-5.1 ms, D = 256 7.2-7.7 -> 7.9-8.1 ms:
+// 40 % fewer ALU operations buy 16 % -- below D = 128 the kernel is bound by the TMEM read-back of the scores (128 KB
+// per tile at ~80-96 B/clk/SM, about 22 scores per clock per SM whatever D is), not by the ALU pipe.  GS = 8 up to
+// padded D = 64 (tc16_group_size), 4 above.
+template <int NKB, int CL, bool BR = false, int GS = 4>
 __global__ void __launch_bounds__(kT16Threads, 1)
     search_tc16_kernel(const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_e,
                        T16Params p) {
@@ -364,7 +371,7 @@ __global__ void __launch_bounds__(kT16Threads, 1)
                     tc_fence_after();
                     const uint32_t t_acc = tmem_base + lane_addr + acc * kTcBN + hsel * 128;
                     const uint32_t hs = hs_base + tj * (kTcBN * 4);
-                    const uint32_t id_base = (uint32_t)(tj * 64 + hsel * 32);
+                    const uint32_t id_base = (uint32_t)(tj * (kTcBN / GS) + hsel * (128 / GS));
                     uint32_t ra[32], rb[32];
                     tmem_ld32_issue(t_acc, ra);
 #pragma unroll
@@ -374,17 +381,26 @@ __global__ void __launch_bounds__(kT16Threads, 1)
                         tmem_ld_wait();
                         if (c0 + 32 < 128) tmem_ld32_issue(t_acc + c0 + 32, rn);
 #pragma unroll
-                        for (int c4 = 0; c4 < 8; ++c4) {
-                            float4 h4;
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                                         : "=f"(h4.x), "=f"(h4.y), "=f"(h4.z), "=f"(h4.w)
-                                         : "r"(hs + (c0 + c4 * 4) * 4));
-                            const float s0 = fmaf(__uint_as_float(r[c4 * 4 + 0]), neg_inv, h4.x);
-                            const float s1 = fmaf(__uint_as_float(r[c4 * 4 + 1]), neg_inv, h4.y);
-                            const float s2 = fmaf(__uint_as_float(r[c4 * 4 + 2]), neg_inv, h4.z);
-                            const float s3 = fmaf(__uint_as_float(r[c4 * 4 + 3]), neg_inv, h4.w);
-                            const float gm = fminf(min3_f32(s0, s1, s2), s3);
-                            const uint32_t gid = id_base + (uint32_t)((c0 >> 2) + c4);
+                        for (int cg = 0; cg < 32 / GS; ++cg) {
+                            float sc[GS];
+#pragma unroll
+                            for (int v = 0; v < GS / 4; ++v) {
+                                float4 h4;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                             : "=f"(h4.x), "=f"(h4.y), "=f"(h4.z), "=f"(h4.w)
+                                             : "r"(hs + (c0 + cg * GS + v * 4) * 4));
+                                sc[4 * v + 0] = fmaf(__uint_as_float(r[cg * GS + v * 4 + 0]), neg_inv, h4.x);
+                                sc[4 * v + 1] = fmaf(__uint_as_float(r[cg * GS + v * 4 + 1]), neg_inv, h4.y);
+                                sc[4 * v + 2] = fmaf(__uint_as_float(r[cg * GS + v * 4 + 2]), neg_inv, h4.z);
+                                sc[4 * v + 3] = fmaf(__uint_as_float(r[cg * GS + v * 4 + 3]), neg_inv, h4.w);
+                            }
+                            float gm;
+                            if constexpr (GS == 4)
+                                gm = fminf(min3_f32(sc[0], sc[1], sc[2]), sc[3]);
+                            else
+                                gm = fminf(min3_f32(min3_f32(sc[0], sc[1], sc[2]), min3_f32(sc[3], sc[4], sc[5]), sc[6]),
+                                           sc[7]);
+                            const uint32_t gid = id_base + (uint32_t)(c0 / GS + cg);
                             const float key = __uint_as_float((__float_as_uint(gm) & 0xffffff00u) | gid);
                             // sorted insert of key into (k1 <= k2 <= k3 <= k4)
                             if (!BR || key < k4) {
@@ -415,7 +431,7 @@ __global__ void __launch_bounds__(kT16Threads, 1)
                 asm volatile("bar.sync 1, %0;" ::"n"(kT16EpiThreads) : "memory");
                 // merge the super-tile's top-4 into the running top-4 (earlier codes win ties)
                 if (k1 < g.v4) {
-                    const int base = st * 256;
+                    const int base = st * (4 * kTcBN / GS);
                     top4_insert(g, k1, base + (int)(__float_as_uint(k1) & 0xffu));
                     top4_insert(g, k2, base + (int)(__float_as_uint(k2) & 0xffu));
                     top4_insert(g, k3, base + (int)(__float_as_uint(k3) & 0xffu));
@@ -454,7 +470,9 @@ __global__ void __launch_bounds__(kT16Threads, 1)
                 const float zn = p.znorm[row], zr = p.zres[row];
                 const float alpha = zr + (zn + zr) * rho16 + p.acc_eps * zn;
                 const float beta0 = (zn + zr) * a16;
-                const float n1 = fminf(__ldg(p.gmax + m.i1), e_max);
+                float n1 = __ldg(p.gmax + m.i1 * (GS / 4));  // gmax: per 4 codes
+                if constexpr (GS == 8) n1 = fmaxf(n1, __ldg(p.gmax + m.i1 * 2 + 1));
+                n1 = fminf(n1, e_max);
                 const float eps1 = alpha * n1 + beta0 + 2.f * p.acc_eps * (0.5f * n1 * n1 + zn * n1);
                 const float U = m.v1 + eps1;
                 const float n0 = fminf(zn + sqrtf(fmaxf(zn * zn + 2.f * U, 0.f)), e_max);
@@ -501,12 +519,18 @@ __device__ __forceinline__ void lex_min(float& s, int& k, float s2, int k2) {
 }
 
 // kExact: D == 32 * NCH, no channel guards (the guards cost the batched immediate-offset loads: 0.52 -> 0.79 ms)
-template <int NCH, bool kExact>
+// GS: codes per candidate group (4 or 8).  A warp owns 4 tokens and keeps 16 (token, code) row streams in flight per
+// step: 4 tokens x 4 codes in one step (GS = 4), or 2 tokens x 8 codes in each of two steps (GS = 8).
+template <int NCH, bool kExact, int GS>
 __global__ void __launch_bounds__(256)
     rescore_groups_kernel(const float* __restrict__ z, const float* __restrict__ E, const float* __restrict__ half_norm,
                           const int32_t* __restrict__ group1, const int32_t* __restrict__ group2,
                           const int32_t* __restrict__ group3, int64_t N, int Dreal, int64_t HW, int K,
                           int64_t* __restrict__ idx_out, float* __restrict__ dmin_out) {
+    static_assert(GS == 4 || GS == 8, "group size");
+    constexpr int TPS = 16 / GS;   // tokens per step
+    constexpr int STEPS = 4 / TPS;
+    constexpr int LPT = 2 * GS;    // lanes per token after the butterfly
     constexpr int DT = 32 * NCH;  // D rounded up to 32; tile rows >= D are zeros
     const int D = kExact ? DT : Dreal;  // a compile-time constant in the exact instantiations
     // row stride 36 floats: the 4 tokens of a warp are one aligned 16-byte read, stores stay conflict-free
@@ -529,127 +553,134 @@ __global__ void __launch_bounds__(256)
     }
     const int lane = tx, r0 = ty * 4;
     int g1[4], g2[4];
-    const float* row[16];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
         const int64_t tok = t0 + r0 + t;
         const bool ok = tok < N;
         g1[t] = ok ? __ldg(group1 + tok) : 0;
         g2[t] = ok ? __ldg(group2 + tok) : -1;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            int k = g1[t] * 4 + c;
-            k = k < K ? k : K - 1;  // rows past the end are read in bounds and discarded below
-            row[t * 4 + c] = E + (size_t)k * D + lane;
-        }
     }
     __syncthreads();
-    float acc[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int st = 0; st < STEPS; ++st) {
+        const float* row[16];
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        const float4 z4 = *reinterpret_cast<const float4*>(&tile[32 * c + lane][r0]);
-        const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
-        if (kExact || 32 * c + lane < D) {  // only the last block of a D that is not a multiple of 32 is partial
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] = fmaf(zv[j >> 2], __ldg(row[j] + 32 * c), acc[j]);
+        for (int j = 0; j < 16; ++j) {
+            int k = g1[st * TPS + j / GS] * GS + (j % GS);
+            k = k < K ? k : K - 1;  // rows past the end are read in bounds and discarded below
+            row[j] = E + (size_t)k * D + lane;
         }
-    }
-    // transposed butterfly: afterwards lane L holds the full sum of accumulator (L >> 1) & 15
-    {
-        const bool up = lane & 16;
+        float acc[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float keep = up ? acc[j + 8] : acc[j], send = up ? acc[j] : acc[j + 8];
-            acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-    }
-    {
-        const bool up = lane & 8;
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float keep = up ? acc[j + 4] : acc[j], send = up ? acc[j] : acc[j + 4];
-            acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    {
-        const bool up = lane & 4;
+        for (int c = 0; c < NCH; ++c) {
+            const float4 z4 = *reinterpret_cast<const float4*>(&tile[32 * c + lane][r0]);
+            const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
+            if (kExact || 32 * c + lane < D) {  // only the last block of a D that is not a multiple of 32 is partial
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const float keep = up ? acc[j + 2] : acc[j], send = up ? acc[j] : acc[j + 2];
-            acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                for (int j = 0; j < 16; ++j) acc[j] = fmaf(zv[st * TPS + j / GS], __ldg(row[j] + 32 * c), acc[j]);
+            }
         }
-    }
-    {
-        const bool up = lane & 2;
-        const float keep = up ? acc[1] : acc[0], send = up ? acc[0] : acc[1];
-        acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    const float dot = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
-    const int my_t = lane >> 3, my_c = (lane >> 1) & 3;  // token / code within the group of this lane's sum
-    const int my_g1 = my_t == 0 ? g1[0] : (my_t == 1 ? g1[1] : (my_t == 2 ? g1[2] : g1[3]));
-    int best_k = my_g1 * 4 + my_c;
-    float best = INFINITY;
-    if (best_k < K) {
-        best = __ldg(half_norm + best_k) - dot;
-        if (best != best) {  // NaN scores never win
-            best = INFINITY;
+        // transposed butterfly: afterwards lane L holds the full sum of accumulator (L >> 1) & 15
+        {
+            const bool up = lane & 16;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float keep = up ? acc[j + 8] : acc[j], send = up ? acc[j] : acc[j + 8];
+                acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+        }
+        {
+            const bool up = lane & 8;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float keep = up ? acc[j + 4] : acc[j], send = up ? acc[j] : acc[j + 4];
+                acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+        }
+        {
+            const bool up = lane & 4;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float keep = up ? acc[j + 2] : acc[j], send = up ? acc[j] : acc[j + 2];
+                acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+        }
+        {
+            const bool up = lane & 2;
+            const float keep = up ? acc[1] : acc[0], send = up ? acc[0] : acc[1];
+            acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+        const float dot = acc[0] + __shfl_xor_sync(0xffffffffu, acc[0], 1);
+        const int my_t = lane / LPT, my_c = (lane >> 1) & (GS - 1);  // token / code within the group of this lane's sum
+        int my_g1 = g1[st * TPS];
+#pragma unroll
+        for (int t = 1; t < TPS; ++t) my_g1 = my_t == t ? g1[st * TPS + t] : my_g1;
+        int best_k = my_g1 * GS + my_c;
+        float best = INFINITY;
+        if (best_k < K) {
+            best = __ldg(half_norm + best_k) - dot;
+            if (best != best) {  // NaN scores never win
+                best = INFINITY;
+                best_k = 0x7fffffff;
+            }
+        } else {
             best_k = 0x7fffffff;
         }
-    } else {
-        best_k = 0x7fffffff;
-    }
-    // (score, index) lexicographic minimum over the 4 codes of the token (lane bits 1 and 2)
+        // (score, index) lexicographic minimum over the GS codes of the token (lane bits 1 .. log2(GS))
 #pragma unroll
-    for (int o = 2; o <= 4; o <<= 1) {
-        const float s2 = __shfl_xor_sync(0xffffffffu, best, o);
-        const int k2 = __shfl_xor_sync(0xffffffffu, best_k, o);
-        lex_min(best, best_k, s2, k2);
-    }
-    // slow path: tokens with more candidate groups (warp-uniform branches)
+        for (int o = 2; o <= GS; o <<= 1) {
+            const float s2 = __shfl_xor_sync(0xffffffffu, best, o);
+            const int k2 = __shfl_xor_sync(0xffffffffu, best_k, o);
+            lex_min(best, best_k, s2, k2);
+        }
+        // slow path: tokens with more candidate groups (warp-uniform branches)
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        if (g2[t] < 0) continue;
-        const int64_t tok = t0 + r0 + t;
-        float b = __shfl_sync(0xffffffffu, best, t * 8);
-        int bk = __shfl_sync(0xffffffffu, best_k, t * 8);
+        for (int t = 0; t < TPS; ++t) {
+            if (g2[st * TPS + t] < 0) continue;
+            const int64_t tok = t0 + r0 + st * TPS + t;
+            float b = __shfl_sync(0xffffffffu, best, t * LPT);
+            int bk = __shfl_sync(0xffffffffu, best_k, t * LPT);
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            const int grp = pass == 0 ? g2[t] : __ldg(group3 + tok);
-            if (grp < 0) break;
-            const int k0 = grp * 4;
-            float a4[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int d = lane; d < D; d += 32) {
-                const float zv = tile[d][r0 + t];
+            for (int pass = 0; pass < 2; ++pass) {
+                const int grp = pass == 0 ? g2[st * TPS + t] : __ldg(group3 + tok);
+                if (grp < 0) break;
+                const int k0 = grp * GS;
+                float a4[GS];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < GS; ++c) a4[c] = 0.f;
+                for (int d = lane; d < D; d += 32) {
+                    const float zv = tile[d][r0 + st * TPS + t];
+#pragma unroll
+                    for (int c = 0; c < GS; ++c) {
+                        const int k = k0 + c;
+                        a4[c] = fmaf(zv, (k < K) ? __ldg(E + (size_t)k * D + d) : 0.f, a4[c]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < GS; ++c) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) a4[c] += __shfl_xor_sync(0xffffffffu, a4[c], o);
                     const int k = k0 + c;
-                    a4[c] = fmaf(zv, (k < K) ? __ldg(E + (size_t)k * D + d) : 0.f, a4[c]);
+                    if (k < K) {
+                        const float dsc = __ldg(half_norm + k) - a4[c];
+                        if (dsc == dsc) lex_min(b, bk, dsc, k);
+                    }
                 }
             }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) a4[c] += __shfl_xor_sync(0xffffffffu, a4[c], o);
-                const int k = k0 + c;
-                if (k < K) {
-                    const float dsc = __ldg(half_norm + k) - a4[c];
-                    if (dsc == dsc) lex_min(b, bk, dsc, k);
-                }
+            if (lane / LPT == t) {
+                best = b;
+                best_k = bk;
             }
         }
-        if ((lane >> 3) == t) {
-            best = b;
-            best_k = bk;
-        }
-    }
-    if ((lane & 7) == 0) {
-        const int64_t tok = t0 + r0 + my_t;
-        if (tok < N) {
-            if (best_k == 0x7fffffff) best_k = my_g1 * 4 < K ? my_g1 * 4 : 0;
-            idx_out[tok] = best_k;
-            if (dmin_out) dmin_out[tok] = best;
+        if ((lane & (LPT - 1)) == 0) {
+            const int64_t tok = t0 + r0 + st * TPS + my_t;
+            if (tok < N) {
+                if (best_k == 0x7fffffff) best_k = my_g1 * GS < K ? my_g1 * GS : 0;
+                idx_out[tok] = best_k;
+                if (dmin_out) dmin_out[tok] = best;
+            }
         }
     }
 }
@@ -712,17 +743,24 @@ size_t search_tc16_workspace_bytes(int64_t n_tokens, int D, int K) {
 
 VQB_KNOB g_tc16_cluster = 2;
 VQB_KNOB g_tc16_branchy = 0;  // vqb_tune "tc16_branchy": conditional top-4 insert in the epilogue (cluster 2 only)
+VQB_KNOB g_tc16_group = 0;    // vqb_tune "tc16_group": 0 = tc16_group_size(Dpad), 4 or 8 = forced (cluster 2, Dpad <= 256)
 #ifdef VQB_EXPERIMENTAL
 void set_tc16_cluster(int c) {
-    if (c >= 16) g_tc16_branchy = c - 16; else g_tc16_cluster = c;
+    if (c >= 32) g_tc16_group = c - 32; else if (c >= 16) g_tc16_branchy = c - 16; else g_tc16_cluster = c;
 }
 #endif
 
-template <int NKB, int CL, bool BR = false>
+// codes per candidate group: 8 where the epilogue, not the tensor pipe, bounds the kernel (see search_tc16_kernel)
+static int tc16_group_size(int Dpad) {
+    if (g_tc16_group == 4 || g_tc16_group == 8) return Dpad <= 256 ? g_tc16_group : 4;
+    return Dpad <= kTc16WideGroupDpad ? 8 : 4;
+}
+
+template <int NKB, int CL, bool BR = false, int GS = 4>
 static int launch_tc16_cl(const CUtensorMap& mz, const CUtensorMap& me, const T16Params& p, cudaStream_t s) {
     constexpr int kStages = tc16_stages(NKB);
     const size_t smem = 1024 + NKB * kTcABlockBytes + (size_t)kStages * kTcBStageBytes + kTcBarrierBytes + 12288;
-    VQB_CUDA_TRY(cudaFuncSetAttribute(search_tc16_kernel<NKB, CL, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    VQB_CUDA_TRY(cudaFuncSetAttribute(search_tc16_kernel<NKB, CL, BR, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     const int n_m_tiles = (int)((p.N + kTcBM - 1) / kTcBM);
     int grid = n_m_tiles < sm_count() ? n_m_tiles : sm_count();
@@ -744,19 +782,27 @@ static int launch_tc16_cl(const CUtensorMap& mz, const CUtensorMap& me, const T1
         // persistent kernel: never launch more clusters than can be co-resident (GPC granularity
         // strands some SMs for larger clusters)
         int max_clusters = 0;
-        VQB_CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, search_tc16_kernel<NKB, CL, BR>, &cfg));
+        VQB_CUDA_TRY(cudaOccupancyMaxActiveClusters(&max_clusters, search_tc16_kernel<NKB, CL, BR, GS>, &cfg));
         if (max_clusters > 0 && grid > max_clusters * CL) {
             grid = max_clusters * CL;
             cfg.gridDim = dim3((unsigned)grid);
         }
     }
-    VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_tc16_kernel<NKB, CL, BR>, mz, me, p));
+    VQB_CUDA_TRY(cudaLaunchKernelEx(&cfg, search_tc16_kernel<NKB, CL, BR, GS>, mz, me, p));
     return VQB_OK;
 }
 
 template <int NKB>
 static int launch_tc16_t(const CUtensorMap& mz, const CUtensorMap& me1, const CUtensorMap& me2, const CUtensorMap& me4,
-                         const T16Params& p, cudaStream_t s) {
+                         const T16Params& p, cudaStream_t s, int gs) {
+#ifdef VQB_EXPERIMENTAL
+    constexpr bool kWide = true;  // measurement build: either group size at any Dpad <= 256 (A/B)
+#else
+    constexpr bool kWide = NKB * kTcBK <= kTc16WideGroupDpad;
+#endif
+    if constexpr (kWide) {
+        if (gs == 8) return launch_tc16_cl<NKB, 2, false, 8>(mz, me2, p, s);
+    }
     switch (g_tc16_cluster) {
         case 1: return launch_tc16_cl<NKB, 1>(mz, me1, p, s);
         case 4: return launch_tc16_cl<NKB, 4>(mz, me4, p, s);
@@ -850,11 +896,12 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
     p.full_count = counts + 0;
     p.acc_eps = D > 256 ? 1.f / 16384.f : 1.f / 32768.f;
     int rc;
+    const int gs = tc16_group_size(Dpad);
     switch (Dpad / kTcBK) {
-        case 1: rc = launch_tc16_t<1>(mz, me1, me2, me4, p, s); break;
-        case 2: rc = launch_tc16_t<2>(mz, me1, me2, me4, p, s); break;
-        case 3: rc = launch_tc16_t<3>(mz, me1, me2, me4, p, s); break;
-        case 4: rc = launch_tc16_t<4>(mz, me1, me2, me4, p, s); break;
+        case 1: rc = launch_tc16_t<1>(mz, me1, me2, me4, p, s, gs); break;
+        case 2: rc = launch_tc16_t<2>(mz, me1, me2, me4, p, s, gs); break;
+        case 3: rc = launch_tc16_t<3>(mz, me1, me2, me4, p, s, gs); break;
+        case 4: rc = launch_tc16_t<4>(mz, me1, me2, me4, p, s, gs); break;
         // 256 < D <= 512: the resident token tile takes 80-128 KB, 4-2 codebook stages remain; clusters of 2 only
         case 5: rc = launch_tc16_cl<5, 2>(mz, me2, p, s); break;
         case 6: rc = launch_tc16_cl<6, 2>(mz, me2, p, s); break;
@@ -868,22 +915,29 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
     // exact fp32 choice among the 4 (or 8) certified candidates of every token
     {
         const unsigned blocks = (unsigned)((N + 31) / 32);
-#define VQB_RESCORE(nch)                                                                                                \
+#define VQB_RESCORE_G(nch, ex, g)                                                                                       \
     do {                                                                                                                \
         constexpr int kSm = (nch) * 32 * 36 * (int)sizeof(float);                                                       \
-        if (D == 32 * (nch)) {                                                                                          \
-            if (kSm > 48 * 1024)                                                                                        \
-                VQB_CUDA_TRY(cudaFuncSetAttribute(rescore_groups_kernel<nch, true>,                                     \
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));                   \
-            rescore_groups_kernel<nch, true><<<blocks, 256, kSm, s>>>(z, E, p.half_norm, p.group1, p.group2, p.group3, N, \
-                                                                      D, HW, K, idx_out, dmin_out);                     \
-        } else {                                                                                                        \
-            if (kSm > 48 * 1024)                                                                                        \
-                VQB_CUDA_TRY(cudaFuncSetAttribute(rescore_groups_kernel<nch, false>,                                    \
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));                   \
-            rescore_groups_kernel<nch, false><<<blocks, 256, kSm, s>>>(z, E, p.half_norm, p.group1, p.group2, p.group3,  \
-                                                                       N, D, HW, K, idx_out, dmin_out);                 \
+        if (kSm > 48 * 1024)                                                                                            \
+            VQB_CUDA_TRY(cudaFuncSetAttribute(rescore_groups_kernel<nch, ex, g>,                                        \
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));                       \
+        rescore_groups_kernel<nch, ex, g><<<blocks, 256, kSm, s>>>(z, E, p.half_norm, p.group1, p.group2, p.group3, N,   \
+                                                                   D, HW, K, idx_out, dmin_out);                        \
+    } while (0)
+#ifdef VQB_EXPERIMENTAL
+    constexpr int kWideNch = 8;
+#else
+    constexpr int kWideNch = kTc16WideGroupDpad / 32;
+#endif
+#define VQB_RESCORE(nch)                                                                                                \
+    do {                                                                                                                \
+        if constexpr ((nch) <= kWideNch) {                                                                              \
+            if (gs == 8) {                                                                                              \
+                if (D == 32 * (nch)) VQB_RESCORE_G(nch, true, 8); else VQB_RESCORE_G(nch, false, 8);                    \
+                break;                                                                                                  \
+            }                                                                                                           \
         }                                                                                                               \
+        if (D == 32 * (nch)) VQB_RESCORE_G(nch, true, 4); else VQB_RESCORE_G(nch, false, 4);                            \
     } while (0)
         switch ((D + 31) / 32) {
             case 1: VQB_RESCORE(1); break;
@@ -904,6 +958,7 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
             default: VQB_RESCORE(16); break;
         }
 #undef VQB_RESCORE
+#undef VQB_RESCORE_G
     }
     VQB_LAUNCH_CHECK("rescore_groups_kernel");
     // ambiguous tokens: full exact fp32 search

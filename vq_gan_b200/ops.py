@@ -599,6 +599,42 @@ def _conv1x1_setup(ctx, inputs, output):
     ctx.algo = algo
 
 
+PROFILE_CONV_DW = None
+
+
+def conv1x1_param_grads(gy: Tensor, x: Tensor, want_w: bool = True, want_b: bool = True):
+    """(dW[Cout, Cin], dbias[Cout]) of the 1x1 convolution: dW[o, c] = sum over tokens gy[b, o, t] x[b, c, t], a
+    tokens-long reduction.  This library's 3xTF32 tcgen05 kernel (vqb_conv1x1_dw_f32: both operands by TMA straight from
+    NCHW, dbias summed on the way) for Cin % 16 == 0, Cout <= 256, HW >= 32, HW % 4 == 0; other shapes keep the plain
+    library GEMM (torch) -- there is no slow path inside the library."""
+    _need_cuda_f32(gy, "gy")
+    _need_cuda_f32(x, "x")
+    gy = gy.contiguous()
+    x = x.contiguous()
+    B, Cout, Cin = int(gy.shape[0]), int(gy.shape[1]), int(x.shape[1])
+    HW = x.numel() // max(B * Cin, 1)
+    if want_w and B * HW > 0 and lib().vqb_conv1x1_dw_supported(Cin, Cout, HW):
+        with _on(x.device):
+            gw = torch.zeros((Cout, Cin), dtype=torch.float32, device=x.device)
+            gb = torch.zeros((Cout,), dtype=torch.float32, device=x.device) if want_b else None
+            prof = PROFILE_CONV_DW
+            if prof is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            check(lib().vqb_conv1x1_dw_f32(_p(gy), _p(x), B, Cin, Cout, HW, _p(gw), _p(gb), _stream()), "vqb_conv1x1_dw_f32")
+            if prof is not None:
+                ev1.record()
+                prof.append((ev0, ev1))
+            _count("conv", 1)
+        return gw, gb
+    gw = gb = None
+    if want_w:
+        gw = torch.einsum("bot,bct->oc", gy.reshape(B, Cout, -1), x.reshape(B, Cin, -1))
+    if want_b:
+        gb = gy.reshape(B, Cout, -1).sum(dim=(0, 2))
+    return gw, gb
+
+
 def _conv1x1_bwd(ctx, gy):
     x, weight = ctx.saved_tensors
     w2 = weight.reshape(weight.shape[0], -1)
@@ -610,12 +646,12 @@ def _conv1x1_bwd(ctx, gy):
         cin_t, cout_t = int(w2.shape[0]), int(w2.shape[1])
         algo_t = ctx.algo if (ctx.algo != 1 or (cin_t % 32 == 0 and cout_t % 16 == 0 and cout_t <= 256)) else 0
         gx = conv1x1(gy, w2.t().contiguous(), None, algo_t)
-    if ctx.needs_input_grad[1]:
-        # dW[o, c] = sum over tokens dy[o, t] x[c, t]: a tokens-long reduction; plain library GEMM (torch)
-        B, Cout = gy.shape[0], gy.shape[1]
-        gw = torch.einsum("bot,bct->oc", gy.reshape(B, Cout, -1), x.reshape(B, x.shape[1], -1)).reshape(weight.shape)
-    if ctx.has_bias and ctx.needs_input_grad[2]:
-        gb = gy.reshape(gy.shape[0], gy.shape[1], -1).sum(dim=(0, 2))
+    want_w = ctx.needs_input_grad[1]
+    want_b = ctx.has_bias and ctx.needs_input_grad[2]
+    if want_w or want_b:
+        gw, gb = conv1x1_param_grads(gy, x, want_w, want_b)
+        gw = gw.reshape(weight.shape) if want_w else None
+        gb = gb if want_b else None
     return gx, gw, gb, None
 
 
