@@ -108,5 +108,37 @@ for case in range(n_cases):
         if not r < 3e-6:
             print(f"FAIL case {case} conv Cin={D} Cout={Cout} B={B} HW={HW}: {r:.3e}", flush=True)
             fails += 1
+        # its parameter gradients (the tcgen05 reduction kernel where the shape qualifies, the library GEMM elsewhere)
+        gy = torch.randn(B, Cout, HW, generator=g) * float(rng.choice([1.0, 1e-3]))
+        gw, gb = ops.conv1x1_param_grads(gy.cuda(), zc)
+        wref = torch.einsum("bot,bct->oc", gy.double(), z.double())
+        wbound = torch.einsum("bot,bct->oc", gy.abs().double(), z.abs().double())
+        r = float(((gw.cpu().double() - wref).abs() / wbound.clamp_min(1e-300)).max())
+        rb = float(((gb.cpu().double() - gy.double().sum(dim=(0, 2))).abs() / gy.abs().double().sum(dim=(0, 2)).clamp_min(1e-300)).max())
+        if not (r < 4e-6 and rb < 4e-6):
+            print(f"FAIL case {case} conv dW Cin={D} Cout={Cout} B={B} HW={HW}: dW {r:.3e} dbias {rb:.3e}", flush=True)
+            fails += 1
+    # GroupNorm + SiLU, forward and backward, against float64
+    if case % 3 == 0:
+        G = int(rng.choice([1, 2, 4, 8]))
+        cpg = int(rng.choice([1, 2, 3, 8, 16]))
+        C = G * cpg
+        hw = int(rng.choice([4, 36, 49, 256, 1024, 1225, 2304, 4096]))
+        x = (torch.randn(B, C, hw, generator=g) * 2 + 0.5)
+        wt, bt = 1 + 0.3 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+        gyn = torch.randn(B, C, hw, generator=g)
+        y, mean, rstd = ops.groupnorm_silu(x.cuda(), wt.cuda(), bt.cuda(), G, 1e-6)
+        dx, dw_, db_ = ops.groupnorm_silu_backward(gyn.cuda(), x.cuda(), wt.cuda(), bt.cuda(), mean, rstd, G)
+        xr = x.double().requires_grad_(True)
+        wr, br = wt.double().requires_grad_(True), bt.double().requires_grad_(True)
+        yr = torch.nn.functional.silu(torch.nn.functional.group_norm(xr, G, wr, br, 1e-6))
+        yr.backward(gyn.double())
+        e_y = float((y.cpu().double() - yr.detach()).abs().max())
+        e_dx = float((dx.cpu().double() - xr.grad).abs().max() / xr.grad.abs().max().clamp_min(1e-30))
+        e_dw = float((dw_.cpu().double() - wr.grad).abs().max() / wr.grad.abs().max().clamp_min(1e-30))
+        e_db = float((db_.cpu().double() - br.grad).abs().max() / br.grad.abs().max().clamp_min(1e-30))
+        if not (e_y < 2e-5 and e_dx < 1e-4 and e_dw < 1e-4 and e_db < 1e-4):
+            print(f"FAIL case {case} groupnorm B={B} C={C} G={G} HW={hw}: y {e_y:.2e} dx {e_dx:.2e} dw {e_dw:.2e} db {e_db:.2e}", flush=True)
+            fails += 1
 print(f"soak: {n_cases} cases, {fails} failures, {time.time() - t_start:.1f} s")
 sys.exit(1 if fails else 0)

@@ -9,12 +9,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 SHAPES = [
-    (4, 256, 256, 32, 32),   # the default VQGAN bottleneck: two 128-row tiles, two 128-channel chunks
+    (4, 256, 256, 32, 32),   # the default VQGAN bottleneck: two 128-row tiles x one 256-channel chunk
     (3, 128, 64, 16, 16),    # one tile, one chunk
     (5, 32, 16, 6, 6),       # HW = 36: a partial last token block (TMA zero fill)
-    (2, 192, 200, 8, 8),     # Cout not a multiple of 128 (the second tile's box runs into the next image), chunk 96
-    (2, 320, 48, 8, 8),      # chunk 80 (not a multiple of 32: the last TMEM read is partly unused)
-    (2, 512, 256, 16, 16),   # four chunks
+    (2, 192, 200, 8, 8),     # Cout not a multiple of 128 (the second tile's box runs into the next image), chunk 192
+    (2, 320, 48, 8, 8),      # chunk 160 (a multiple of 32); see (2, 80, 48, 8, 8) for a partly unused last TMEM read
+    (2, 512, 256, 16, 16),   # two chunks x two tiles
+    (2, 80, 48, 8, 8),       # chunk 80: the last 32-column TMEM read is half unused
+    (2, 768, 32, 8, 8),      # three chunks
     (3, 16, 1, 8, 8),        # one output channel
     (1, 64, 4, 128, 128),    # one image, many token blocks per CTA
 ]

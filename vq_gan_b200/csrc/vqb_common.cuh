@@ -214,5 +214,6 @@ void tc16_split_pointers(void* ws, int64_t N, int D, __half** z16, float** inv_s
 void set_lowd_variant(int v);
 void set_tc16_cluster(int c);
 void set_norm_cluster(int v);
+void set_dw_hw_trunc(int v);
 
 }  // namespace vqb

@@ -5,11 +5,13 @@
 // token, 2 Cin Cout flop per token.  In NCHW both operands are already K-major for that product -- for a fixed (image,
 // channel) the tokens are contiguous -- so TMA drops [channels x 32 tokens] boxes of dy and x straight into
 // 128B-swizzled shared memory, no transposing converter as in the forward kernel.  3xTF32 for fp32-level accuracy
-// (dyh.xh + dyl.xh + dyh.xl): eight converter warps rewrite each landed tile in place as its tf32-rounded image and
-// write the rounding residual next to it (an elementwise pass: the swizzle does not matter), and sum dy for dbias on
-// the way.  One persistent CTA per SM accumulates its share of the token blocks in TMEM (Cout <= 256 rows as one or two
-// 128-lane tiles, a chunk of <= 128 input channels as columns; blockIdx.y walks the chunks), then adds its partial
-// product to dW with 16-byte reductions (148 partial sums per element: order-dependent in the last bits, like dE).
+// (dyh.xh + dyl.xh + dyh.xl): the landed fp32 tile serves as the hi image as it is (the tensor core ignores the low 13
+// mantissa bits), eight converter warps write the residual image tf32(x - trunc(x)) next to it (an elementwise pass: the
+// swizzle does not matter) and sum dy for dbias on the way.  One persistent CTA per SM accumulates its share of the
+// token blocks in TMEM: a 128-row tile of Cout as lanes, a chunk of <= 256 input channels as columns (blockIdx.y walks
+// the (chunk, tile) pairs; 128 x 256 x 8 MMAs read 12 KB of operands per 128 tensor cycles, 128 x 128 x 8 ones the SM's
+// whole 128 B/clk -- shared-memory bandwidth is what bounds this kernel), then adds its partial product to dW with
+// 16-byte reductions (up to 148 partial sums per element: order-dependent in the last bits, like dE).
 #include "vqb_tc_common.cuh"
 
 namespace vqb {
@@ -29,14 +31,30 @@ __device__ __forceinline__ void dw_umma_tf32(uint32_t tmem_d, uint64_t desc_a, u
         : "memory");
 }
 
+__device__ __forceinline__ float dw_trunc_tf32(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+__device__ __forceinline__ void dw_split(const float4& v, float4& h, float4& l, int hw_trunc) {
+    if (hw_trunc) {
+        h.x = dw_trunc_tf32(v.x); h.y = dw_trunc_tf32(v.y); h.z = dw_trunc_tf32(v.z); h.w = dw_trunc_tf32(v.w);
+    } else {
+        h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+    }
+    l.x = to_tf32(v.x - h.x);
+    l.y = to_tf32(v.y - h.y);
+    l.z = to_tf32(v.z - h.z);
+    l.w = to_tf32(v.w - h.w);
+}
+
 struct DwParams {
     int64_t B, HW;
     int Cin, Cout;
-    int chunk;    // input channels per CTA (columns of the accumulator), multiple of 16, <= 128
-    int m_tiles;  // 1 (Cout <= 128) or 2
+    int chunk;    // input channels per CTA (columns of the accumulator, the MMA's N), multiple of 16, <= 256
+    int m_tiles;  // 128-row tiles of Cout: 1 or 2; blockIdx.y = chunk index * m_tiles + tile
     int stages;
     float* dW;     // [Cout, Cin], accumulated into
     float* dbias;  // [Cout] or null, accumulated into
+    int hw_trunc;  // 1 (default): the landed fp32 tile IS the hi image -- the tensor core ignores the low 13 mantissa
+                   // bits (measured: same 7e-7 error as explicit rounding) -- and only lo = tf32(x - trunc(x)) is written;
+                   // 0 (vqb_tune "dw_hw_trunc"): hi = rna tf32(x) rewritten in place as well
 };
 
 __global__ void __launch_bounds__(kDwThreads, 1)
@@ -44,9 +62,9 @@ __global__ void __launch_bounds__(kDwThreads, 1)
     extern __shared__ unsigned char smem_unaligned[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_unaligned) + 1023) &
                                                            ~(uintptr_t)1023);
-    const uint32_t a_bytes = (uint32_t)p.m_tiles * kDwTileBytes;  // dy tile(s): hi image, then lo image
-    const uint32_t b_bytes = kDwTileBytes;                        // x tile (chunk <= 128 rows)
-    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;       // A hi | A lo | B hi | B lo
+    const uint32_t a_bytes = kDwTileBytes;                                   // dy tile: 128 rows (this CTA's slice of Cout)
+    const uint32_t b_bytes = (p.chunk > 128 ? 2u : 1u) * kDwTileBytes;        // x tile: chunk rows
+    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;                  // A hi | A lo | B hi | B lo
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* raw_full = bars + 0;                   // [stages] TMA -> converters
     uint64_t* cv_full = bars + kDwMaxStages;         // [stages] converters -> MMA
@@ -58,7 +76,9 @@ __global__ void __launch_bounds__(kDwThreads, 1)
     const int64_t kb_per_img = (p.HW + kDwTok - 1) / kDwTok;
     const int64_t total_kb = p.B * kb_per_img;
     const int64_t n_local = blockIdx.x < total_kb ? (total_kb - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int c_base = blockIdx.y * p.chunk;
+    const int mt = (int)blockIdx.y % p.m_tiles;
+    const int c_base = ((int)blockIdx.y / p.m_tiles) * p.chunk;
+    const int o_base = mt * 128;
     const int a_rows = p.Cout < 128 ? p.Cout : 128;  // rows per dy box
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.chunk >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
@@ -84,7 +104,7 @@ __global__ void __launch_bounds__(kDwThreads, 1)
     if (warp == 0) {
         // ===================== TMA producer: raw dy / x boxes =====================
         if (lane == 0) {
-            const uint32_t tx_bytes = (uint32_t)p.m_tiles * (uint32_t)a_rows * 128u + (uint32_t)p.chunk * 128u;
+            const uint32_t tx_bytes = (uint32_t)a_rows * 128u + (uint32_t)p.chunk * 128u;
             for (int64_t it = 0; it < n_local; ++it) {
                 const int64_t kb = blockIdx.x + it * gridDim.x;
                 const uint32_t stage = (uint32_t)(it % p.stages), ph = (uint32_t)((it / p.stages) & 1);
@@ -94,8 +114,7 @@ __global__ void __launch_bounds__(kDwThreads, 1)
                 const int h0 = (int)(kb - b * kb_per_img) * kDwTok;
                 unsigned char* ahi = smem + (size_t)stage * stage_bytes;
                 unsigned char* bhi = ahi + 2 * a_bytes;
-                for (int mt = 0; mt < p.m_tiles; ++mt)
-                    tma_load_2d(ahi + mt * kDwTileBytes, &map_dy, raw_full + stage, h0, (int)(b * p.Cout) + mt * 128);
+                tma_load_2d(ahi, &map_dy, raw_full + stage, h0, (int)(b * p.Cout) + o_base);
                 tma_load_2d(bhi, &map_x, raw_full + stage, h0, (int)(b * p.Cin) + c_base);
             }
         }
@@ -114,27 +133,23 @@ __global__ void __launch_bounds__(kDwThreads, 1)
                 for (int k4 = 0; k4 < kDwTok / 8; ++k4) {  // 8 tf32 = 32 bytes per MMA
                     const uint32_t accum = (it != 0 || k4 != 0) ? 1u : 0u;
                     const uint64_t dbh = umma_desc_sw128(bhi + k4 * 32), dbl = umma_desc_sw128(blo + k4 * 32);
-                    for (int mt = 0; mt < p.m_tiles; ++mt) {
-                        const uint32_t d = tmem_base + (uint32_t)mt * 128u;
-                        const uint64_t dah = umma_desc_sw128(ahi + mt * kDwTileBytes + k4 * 32);
-                        const uint64_t dal = umma_desc_sw128(alo + mt * kDwTileBytes + k4 * 32);
-                        dw_umma_tf32(d, dah, dbh, idesc, accum);
-                        dw_umma_tf32(d, dal, dbh, idesc, 1);
-                        dw_umma_tf32(d, dah, dbl, idesc, 1);
-                    }
+                    const uint64_t dah = umma_desc_sw128(ahi + k4 * 32), dal = umma_desc_sw128(alo + k4 * 32);
+                    dw_umma_tf32(tmem_base, dah, dbh, idesc, accum);
+                    dw_umma_tf32(tmem_base, dal, dbh, idesc, 1);
+                    dw_umma_tf32(tmem_base, dah, dbl, idesc, 1);
                 }
                 umma_commit(s_empty + stage);
             }
             if (n_local > 0) umma_commit(acc_full);
         }
     } else if (warp >= 4 && warp < 12) {
-        // ===================== converters: raw fp32 -> tf32 image in place + residual image; dbias sums ==========
+        // ===================== converters: residual image (and, hw_trunc = 0, the rounded hi image); dbias sums ====
         const int t = threadIdx.x - 128;  // 0..255
-        const uint32_t a_chunks = (uint32_t)(p.Cout < 128 ? p.Cout : p.m_tiles * 128) * 8u;  // 16-byte pieces of the dy tile(s)
+        const uint32_t a_chunks = (uint32_t)a_rows * 8u;  // 16-byte pieces of the dy tile
         const uint32_t b_chunks = (uint32_t)p.chunk * 8u;
-        float bsum[8];  // piece id = t + 256 j -> row (t >> 3) + 32 j: the same rows for every token block
+        float bsum[4];  // piece id = t + 256 j -> row (t >> 3) + 32 j: the same rows for every token block
 #pragma unroll
-        for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+        for (int j = 0; j < 4; ++j) bsum[j] = 0.f;
         for (int64_t it = 0; it < n_local; ++it) {
             const uint32_t stage = (uint32_t)(it % p.stages), ph = (uint32_t)((it / p.stages) & 1);
             tc_mbar_wait(raw_full + stage, ph);
@@ -143,45 +158,39 @@ __global__ void __launch_bounds__(kDwThreads, 1)
             unsigned char* bhi = ahi + 2 * a_bytes;
             unsigned char* blo = bhi + b_bytes;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
                 const uint32_t id = (uint32_t)t + 256u * j;
                 if (id < a_chunks) {
                     const float4 v = *reinterpret_cast<const float4*>(ahi + 16u * id);
                     bsum[j] += (v.x + v.y) + (v.z + v.w);
                     float4 h, l;
-                    h.x = to_tf32(v.x); l.x = to_tf32(v.x - h.x);
-                    h.y = to_tf32(v.y); l.y = to_tf32(v.y - h.y);
-                    h.z = to_tf32(v.z); l.z = to_tf32(v.z - h.z);
-                    h.w = to_tf32(v.w); l.w = to_tf32(v.w - h.w);
-                    *reinterpret_cast<float4*>(ahi + 16u * id) = h;
+                    dw_split(v, h, l, p.hw_trunc);
+                    if (!p.hw_trunc) *reinterpret_cast<float4*>(ahi + 16u * id) = h;
                     *reinterpret_cast<float4*>(alo + 16u * id) = l;
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 8; ++j) {
                 const uint32_t id = (uint32_t)t + 256u * j;
                 if (id < b_chunks) {
                     const float4 v = *reinterpret_cast<const float4*>(bhi + 16u * id);
                     float4 h, l;
-                    h.x = to_tf32(v.x); l.x = to_tf32(v.x - h.x);
-                    h.y = to_tf32(v.y); l.y = to_tf32(v.y - h.y);
-                    h.z = to_tf32(v.z); l.z = to_tf32(v.z - h.z);
-                    h.w = to_tf32(v.w); l.w = to_tf32(v.w - h.w);
-                    *reinterpret_cast<float4*>(bhi + 16u * id) = h;
+                    dw_split(v, h, l, p.hw_trunc);
+                    if (!p.hw_trunc) *reinterpret_cast<float4*>(bhi + 16u * id) = h;
                     *reinterpret_cast<float4*>(blo + 16u * id) = l;
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> tensor-core reads
             tc_mbar_arrive(cv_full + stage);
         }
-        if (p.dbias != nullptr && blockIdx.y == 0) {
+        if (p.dbias != nullptr && c_base == 0) {  // the CTAs of the first channel chunk own dbias (their tile's rows)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
                 float s = bsum[j];
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
                 s += __shfl_xor_sync(0xffffffffu, s, 4);
-                const int row = (t >> 3) + 32 * j;
+                const int row = o_base + (t >> 3) + 32 * j;
                 if ((t & 7) == 0 && row < p.Cout && n_local > 0) atomicAdd(p.dbias + row, s);
             }
         }
@@ -192,23 +201,21 @@ __global__ void __launch_bounds__(kDwThreads, 1)
             const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
             tc_mbar_wait(acc_full, 0);
             tc_fence_after();
-            for (int mt = 0; mt < p.m_tiles; ++mt) {
-                const int o = mt * 128 + q * 32 + lane;
-                const int row_ok = o < p.Cout;
-                float* wp = p.dW + (size_t)(row_ok ? o : 0) * p.Cin + c_base;
-                for (int c0 = 0; c0 < p.chunk; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + lane_addr + (uint32_t)mt * 128u + (uint32_t)c0, r);
+            const int o = o_base + q * 32 + lane;
+            const int row_ok = o < p.Cout;
+            float* wp = p.dW + (size_t)(row_ok ? o : 0) * p.Cin + c_base;
+            for (int c0 = 0; c0 < p.chunk; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + lane_addr + (uint32_t)c0, r);
 #pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
-                            "@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(wp + c0 + 4 * g),
-                            "f"(__uint_as_float(r[4 * g])), "f"(__uint_as_float(r[4 * g + 1])),
-                            "f"(__uint_as_float(r[4 * g + 2])), "f"(__uint_as_float(r[4 * g + 3])),
-                            "r"((int)(row_ok && c0 + 4 * g < p.chunk))
-                            : "memory");
-                }
+                for (int g = 0; g < 8; ++g)
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                        "@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(wp + c0 + 4 * g),
+                        "f"(__uint_as_float(r[4 * g])), "f"(__uint_as_float(r[4 * g + 1])),
+                        "f"(__uint_as_float(r[4 * g + 2])), "f"(__uint_as_float(r[4 * g + 3])),
+                        "r"((int)(row_ok && c0 + 4 * g < p.chunk))
+                        : "memory");
             }
         }
     }
@@ -221,10 +228,10 @@ __global__ void __launch_bounds__(kDwThreads, 1)
     }
 }
 
-// input channels per CTA: the largest multiple of 16 that divides Cin and is <= 128 (0: no tensor path)
+// input channels per CTA: the largest multiple of 16 that divides Cin and is <= 256 (0: no tensor path)
 static int dw_chunk(int Cin) {
     if (Cin < 16 || Cin % 16 != 0) return 0;
-    for (int c = 128; c >= 16; c -= 16)
+    for (int c = 256; c >= 16; c -= 16)
         if (Cin % c == 0) return c;
     return 0;
 }
@@ -232,6 +239,11 @@ static int dw_chunk(int Cin) {
 static bool dw_supported(int Cin, int Cout, int64_t HW) {
     return dw_chunk(Cin) > 0 && Cout >= 1 && Cout <= 256 && HW >= kDwTok && HW % 4 == 0;
 }
+
+VQB_KNOB g_dw_hw_trunc = 1;
+#ifdef VQB_EXPERIMENTAL
+void set_dw_hw_trunc(int v) { g_dw_hw_trunc = v; }
+#endif
 
 }  // namespace vqb
 
@@ -271,14 +283,15 @@ extern "C" int vqb_conv1x1_dw_f32(const float* dy, const float* x, int64_t B, in
     p.m_tiles = Cout > 128 ? 2 : 1;
     p.dW = dW_accum;
     p.dbias = dbias_accum;
-    const size_t stage_bytes = 2 * (size_t)p.m_tiles * kDwTileBytes + 2 * (size_t)kDwTileBytes;
+    p.hw_trunc = g_dw_hw_trunc;
+    const size_t stage_bytes = 2 * (size_t)kDwTileBytes + 2 * (size_t)(p.chunk > 128 ? 2 : 1) * kDwTileBytes;
     int stages = (int)((kTcSmemBudget - 1024 - 512) / stage_bytes);
     p.stages = stages > kDwMaxStages ? kDwMaxStages : stages;
     const size_t smem = 1024 + (size_t)p.stages * stage_bytes + 512;
     CUtensorMap mdy, mx;
     if (int rc = make_tc_map_f32(&mdy, dy, (uint64_t)(B * Cout), (int)HW, (uint32_t)(Cout < 128 ? Cout : 128))) return rc;
     if (int rc = make_tc_map_f32(&mx, x, (uint64_t)(B * Cin), (int)HW, (uint32_t)p.chunk)) return rc;
-    const int n_chunks = Cin / p.chunk;
+    const int n_chunks = (Cin / p.chunk) * p.m_tiles;  // CTA kinds: (channel chunk, 128-row tile of Cout)
     const int64_t total_kb = B * ((HW + kDwTok - 1) / kDwTok);
     int gx = sm_count() / n_chunks;
     if (gx < 1) gx = 1;
