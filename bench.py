@@ -993,6 +993,8 @@ def measure_codebook_variants(args, workload, world, rank, device, kinds=("refin
                      "multi_group_tokens": int(st[2]), "codes_used": int(torch.unique(idx).numel())}
         if int(st[1]) == 6:
             out[kind]["tensor_role_tokens"] = int(st[3])
+        if int(st[1]) == 4:  # of the uncertified tokens, how many the pruned exact tier took (the rest: full fp32 re-search)
+            out[kind]["pruned_tier_tokens"] = int(st[3])
         del E, idx, dmin
     del z
     torch.cuda.empty_cache()

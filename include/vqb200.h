@@ -88,8 +88,10 @@ VQB_API int vqb_codebook_prepare_f32(const float* E, int K, int D, void* pack, s
  * lowest index on ties, NaN rows -> the first NaN code like ATen's argmin.
  * idx_out[N] int64; dmin_out[N] (nullable) receives min_k(0.5|e_k|^2 - z.e_k).
  * stats_out (nullable, int64[4]): [0] tokens fully re-scored in fp32 by a tensor
- * path, [1] algorithm actually used, [2] tokens whose two candidates were
- * re-scored (algo 4), [3] reserved. */
+ * path (no certified winner), [1] algorithm actually used, [2] tokens with two or
+ * three certified candidate groups (algo 4), [3] algo 4: how many of the [0] tokens
+ * the pruned exact tier took (collapsed codebooks; the rest met the full fp32
+ * re-search); algo 6: tokens handled by the tensor role. */
 VQB_API size_t vqb_search_workspace_bytes(int64_t B, int D, int64_t HW, int K, int algo);
 VQB_API int vqb_search_f32(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,
                    const void* pack, int64_t* idx_out, float* dmin_out, void* workspace,

@@ -23,6 +23,7 @@ extern "C" {
  *   "lowd_ctas_per_sm"   0..3   0 = the variant's own residency; 1 leaves room for a co-running kernel
  *   "dual_permille"      0..999 share of the images handed to the tensor role of the two-engine search (algo 6; 0 = model)
  *   "tc16_cluster"       1|2|4  cluster size (codebook-stage multicast) of the fp16 tensor search
+ *   "tc16_pruned"        0|1    pruned exact tier of the fp16 tensor search for long lists of uncertified tokens (default 1)
  *   "tc16_group"         0|4|8  codes per candidate group of the fp16 tensor search (0 = 8 up to padded D 128, 4 above)
  *   "dw_hw_trunc"        0|1    1x1 conv parameter gradients: 1 = the landed fp32 tile is the hi image as it is (relies on the
  *                               tensor core ignoring the low 13 mantissa bits), only the residual image is written

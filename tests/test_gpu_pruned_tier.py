@@ -1,0 +1,88 @@
+"""Pruned exact tier of the fp16 tensor search (csrc/vqb_search_pruned.cu): COLLAPSED codebooks -- many codes a rounding
+error apart, so that no low-precision pass can certify a winner -- must give exactly what the plain fp32 search gives
+(same FMA chain: indices AND minimum scores bit-identical, lowest index on exact ties), whether the tier takes the
+list of uncertified tokens (`stats[3]` = its length) or declines (nothing to prune)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _collapsed(K, D, n_centres, spread, tokens, tok_sigma, seed):
+    g = torch.Generator().manual_seed(seed)
+    centres = torch.randn(n_centres, D, generator=g)
+    E = centres[torch.randint(0, n_centres, (K,), generator=g)] + spread * torch.randn(K, D, generator=g)
+    z = centres[torch.randint(0, n_centres, (tokens,), generator=g)] + tok_sigma * torch.randn(tokens, D, generator=g)
+    return z, E
+
+
+def _as_images(rows, HW):
+    N, D = rows.shape
+    B = N // HW
+    return rows[:B * HW].view(B, HW, D).permute(0, 2, 1).contiguous().view(B, D, HW, 1)
+
+
+@pytest.mark.parametrize("K,D,centres,tokens,HW,expect_tier", [
+    (4096, 64, 8, 16384, 1024, True),     # the tier takes every token
+    (2500, 100, 5, 12288, 256, True),     # K not a multiple of the 128-code tiles, D not a multiple of 32
+    (16384, 256, 16, 8192, 1024, True),   # C3's codebook size
+    (4096, 64, 1, 8192, 1024, False),     # ONE centre: every tile survives for every token, the tier declines
+    (4096, 64, 8, 2048, 1024, False),     # a short list stays with the plain list search
+])
+def test_collapsed_codebook_equals_the_fp32_search(K, D, centres, tokens, HW, expect_tier):
+    from vq_gan_b200 import ops
+    z, E = _collapsed(K, D, centres, 1e-4, tokens, 0.05, seed=K + D)
+    zc, Ec = _as_images(z, HW).cuda(), E.cuda()
+    idx, dmin, st = ops.search(zc, Ec, 4)
+    ref_idx, ref_dmin, _ = ops.search(zc, Ec, 2)
+    st = st.tolist()
+    assert st[1] == 4
+    assert st[0] >= 0.9 * tokens  # nothing certifies on such a codebook
+    assert (st[3] == st[0]) if expect_tier else (st[3] == 0), st
+    assert torch.equal(idx, ref_idx)
+    assert torch.equal(dmin, ref_dmin)
+
+
+def test_exact_duplicates_keep_the_lowest_index():
+    """Whole clusters of IDENTICAL codes: every score ties exactly, the original (unsorted) index decides."""
+    from vq_gan_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    centres = torch.randn(6, 64, generator=g)
+    E = centres[torch.randint(0, 6, (4096,), generator=g)].contiguous()
+    z = centres[torch.randint(0, 6, (8192,), generator=g)] + 0.05 * torch.randn(8192, 64, generator=g)
+    zc, Ec = _as_images(z, 1024).cuda(), E.cuda()
+    idx, dmin, st = ops.search(zc, Ec, 4)
+    ref_idx, ref_dmin, _ = ops.search(zc, Ec, 2)
+    assert st.tolist()[3] == st.tolist()[0] > 0
+    assert torch.equal(idx, ref_idx) and torch.equal(dmin, ref_dmin)
+    # the winner is the FIRST code of the token's cluster
+    first = torch.stack([(E == E[i]).all(dim=1).nonzero()[0, 0] for i in ref_idx.reshape(-1)[:64].cpu()])
+    assert torch.equal(first, ref_idx.reshape(-1)[:64].cpu())
+
+
+def test_nan_and_inf_tokens_and_module_forward():
+    from vq_gan_b200 import VectorQuantizer, ops
+    z, E = _collapsed(4096, 64, 8, 1e-4, 16384, 0.05, seed=7)
+    z[::97] = float("nan")
+    z[5::1013] = float("inf")
+    zc, Ec = _as_images(z, 1024).cuda(), E.cuda()
+    idx, dmin, st = ops.search(zc, Ec, 4)
+    ref_idx, ref_dmin, _ = ops.search(zc, Ec, 2)
+    assert st.tolist()[3] > 0
+    assert torch.equal(idx, ref_idx)
+    assert torch.equal(dmin.nan_to_num(nan=-7.0), ref_dmin.nan_to_num(nan=-7.0))
+    # through the module (automatic kernel choice), forward + backward, against the CPU oracle on clean tokens
+    from oracle import vq_oracle as orc
+    z, E = _collapsed(4096, 64, 8, 1e-4, 16384, 0.05, seed=8)
+    zi = _as_images(z, 1024)
+    vq = VectorQuantizer(4096, 64, 0.25).cuda()
+    with torch.no_grad():
+        vq.embedding.weight.copy_(E)
+    zin = zi.cuda().requires_grad_(True)
+    z_q, loss_dict, indices = vq(zin)
+    loss_dict["vq_loss"].backward()
+    assert vq.last_search_stats.tolist()[1] == 4 and vq.last_search_stats.tolist()[3] > 0
+    rep = orc.compare_indices(indices.reshape(-1).cpu(), orc.search_with_gap(orc.tokens_of(zi), E))
+    assert rep["outside"] == 0, rep
+    fo = orc.forward(zi, E, 0.25, idx=indices.reshape(-1).cpu())
+    assert torch.equal(z_q.detach().cpu(), fo["z_q"])

@@ -22,7 +22,7 @@ OBJDIR = os.path.join(PKG, "build")
 LIB = os.path.join(LIBDIR, "libvqb200.so")
 BENCH_LIB = os.path.join(LIBDIR, "libvqb200_bench.so")
 SOURCES = ["vqb_api.cu", "vqb_prepare.cu", "vqb_search_lowd.cu", "vqb_search_fp32.cu",
-           "vqb_search_tc.cu", "vqb_search_tc16.cu", "vqb_search_tclow.cu", "vqb_tail.cu", "vqb_indexio.cu", "vqb_stats.cu",
+           "vqb_search_tc.cu", "vqb_search_tc16.cu", "vqb_search_pruned.cu", "vqb_search_tclow.cu", "vqb_tail.cu", "vqb_indexio.cu", "vqb_stats.cu",
            "vqb_conv1x1.cu", "vqb_conv1x1_dw.cu", "vqb_norm.cu"]
 BENCH_ONLY_SOURCES = ["vqb_ubench.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -115,6 +115,10 @@ extern "C" int vqb_tune(const char* key, int value) {
         set_norm_cluster(value);
         return VQB_OK;
     }
+    if (strcmp(key, "tc16_pruned") == 0 && (value == 0 || value == 1)) {
+        set_tc16_cluster(64 + value);
+        return VQB_OK;
+    }
     if (strcmp(key, "tc16_group") == 0 && (value == 0 || value == 4 || value == 8)) {
         set_tc16_cluster(32 + value);
         return VQB_OK;

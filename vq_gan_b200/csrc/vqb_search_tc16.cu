@@ -685,21 +685,23 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-__global__ void tc16_stats_kernel(int64_t* stats, const int32_t* full_count, const int32_t* pair_count) {
+// stats[3]: how many of the stats[0] uncertified tokens the pruned exact tier took (the rest met the full re-search)
+__global__ void tc16_stats_kernel(int64_t* stats, const int32_t* full_count, const int32_t* pair_count, const int32_t* handled) {
     stats[0] = *full_count;
     stats[1] = VQB_ALGO_TCGEN05_F16;
     stats[2] = *pair_count;
-    stats[3] = 0;
+    stats[3] = handled ? *handled : 0;
 }
 
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
 struct T16Workspace {
-    size_t off_z16, off_inv, off_znorm, off_zres, off_g1, off_g2, off_g3, off_full, off_counts, off_keys, keys_bytes, total;
+    size_t off_z16, off_inv, off_znorm, off_zres, off_g1, off_g2, off_g3, off_full, off_counts, off_keys, keys_bytes,
+        off_pruned, pruned_bytes, total;
 };
 
-static T16Workspace t16_workspace(int64_t N, int D) {
+static T16Workspace t16_workspace(int64_t N, int D, int K) {
     T16Workspace w;
     size_t off = 0;
     w.off_z16 = off;
@@ -718,17 +720,20 @@ static T16Workspace t16_workspace(int64_t N, int D) {
     off = round_up_z(off + 4 * (size_t)N, 1024);
     w.off_full = off;
     off = round_up_z(off + 4 * (size_t)N, 1024);
-    w.off_counts = off;
-    off += 1024;
+    w.off_counts = off;  // int32[2] (full_count, pair_count) | int32[kPrunedStateInts] at +64 bytes: ONE memset per call
+    off += 2048;
     w.off_keys = off;
     w.keys_bytes = search_fp32_workspace_bytes(N, D);
     off = round_up_z(off + w.keys_bytes, 1024);
+    w.off_pruned = off;  // pruned exact tier (vqb_search_pruned.cu); 0 bytes where it does not apply
+    w.pruned_bytes = search_pruned_workspace_bytes(N, K, D);
+    off = round_up_z(off + w.pruned_bytes, 1024);
     w.total = off;
     return w;
 }
 
 void tc16_split_pointers(void* ws, int64_t N, int D, __half** z16, float** inv_scale, float** znorm, float** zres) {
-    const T16Workspace w = t16_workspace(N, D);
+    const T16Workspace w = t16_workspace(N, D, 0);  // (the split lives in front of everything that depends on K)
     unsigned char* b = static_cast<unsigned char*>(ws);
     *z16 = reinterpret_cast<__half*>(b + w.off_z16);
     *inv_scale = reinterpret_cast<float*>(b + w.off_inv);
@@ -736,17 +741,15 @@ void tc16_split_pointers(void* ws, int64_t N, int D, __half** z16, float** inv_s
     *zres = reinterpret_cast<float*>(b + w.off_zres);
 }
 
-size_t search_tc16_workspace_bytes(int64_t n_tokens, int D, int K) {
-    (void)K;
-    return t16_workspace(n_tokens, D).total;
-}
+size_t search_tc16_workspace_bytes(int64_t n_tokens, int D, int K) { return t16_workspace(n_tokens, D, K).total; }
 
 VQB_KNOB g_tc16_cluster = 2;
 VQB_KNOB g_tc16_branchy = 0;  // vqb_tune "tc16_branchy": conditional top-4 insert in the epilogue (cluster 2 only)
+VQB_KNOB g_tc16_pruned = 1;   // vqb_tune "tc16_pruned": 0 = no pruned exact tier (A/B)
 VQB_KNOB g_tc16_group = 0;    // vqb_tune "tc16_group": 0 = tc16_group_size(Dpad), 4 or 8 = forced (cluster 2, Dpad <= 256)
 #ifdef VQB_EXPERIMENTAL
 void set_tc16_cluster(int c) {
-    if (c >= 32) g_tc16_group = c - 32; else if (c >= 16) g_tc16_branchy = c - 16; else g_tc16_cluster = c;
+    if (c >= 64) g_tc16_pruned = c - 64; else if (c >= 32) g_tc16_group = c - 32; else if (c >= 16) g_tc16_branchy = c - 16; else g_tc16_cluster = c;
 }
 #endif
 
@@ -814,11 +817,41 @@ static int launch_tc16_t(const CUtensorMap& mz, const CUtensorMap& me1, const CU
     }
 }
 
+// exact re-score launch for a D of NCH 32-channel blocks; the wide-group instantiations exist only where tc16_group_size
+// can ask for them (every Dpad <= 256 in the measurement build)
+template <int NCH, bool kExact, int GS>
+static int launch_rescore_g(const float* z, const float* E, const T16Params& p, int64_t N, int D, int64_t HW, int K,
+                            int64_t* idx_out, float* dmin, cudaStream_t s) {
+    constexpr int kSm = NCH * 32 * 36 * (int)sizeof(float);
+    if (kSm > 48 * 1024)
+        VQB_CUDA_TRY(cudaFuncSetAttribute(rescore_groups_kernel<NCH, kExact, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));
+    rescore_groups_kernel<NCH, kExact, GS><<<(unsigned)((N + 31) / 32), 256, kSm, s>>>(z, E, p.half_norm, p.group1, p.group2,
+                                                                                      p.group3, N, D, HW, K, idx_out, dmin);
+    return VQB_OK;
+}
+
+template <int NCH>
+static int launch_rescore(const float* z, const float* E, const T16Params& p, int64_t N, int D, int64_t HW, int K,
+                          int64_t* idx_out, float* dmin, int gs, cudaStream_t s) {
+#ifdef VQB_EXPERIMENTAL
+    constexpr bool kWide = NCH <= 8;
+#else
+    constexpr bool kWide = NCH * 32 <= kTc16WideGroupDpad;
+#endif
+    if constexpr (kWide) {
+        if (gs == 8)
+            return D == 32 * NCH ? launch_rescore_g<NCH, true, 8>(z, E, p, N, D, HW, K, idx_out, dmin, s)
+                                 : launch_rescore_g<NCH, false, 8>(z, E, p, N, D, HW, K, idx_out, dmin, s);
+    }
+    return D == 32 * NCH ? launch_rescore_g<NCH, true, 4>(z, E, p, N, D, HW, K, idx_out, dmin, s)
+                         : launch_rescore_g<NCH, false, 4>(z, E, p, N, D, HW, K, idx_out, dmin, s);
+}
+
 int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float* E, int K, const void* pack,
                        int64_t* idx_out, float* dmin_out, void* ws, size_t ws_bytes, int64_t* stats_out,
                        cudaStream_t s, bool presplit) {
     const int64_t N = B * HW;
-    const T16Workspace w = t16_workspace(N, D);
+    const T16Workspace w = t16_workspace(N, D, K);
     if (!ws || ws_bytes < w.total) {
         set_error("fp16 tensor search workspace too small: %zu < %zu", ws_bytes, w.total);
         return VQB_ERR_WORKSPACE;
@@ -836,7 +869,7 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
     float* zres = reinterpret_cast<float*>(wsb + w.off_zres);
     int32_t* counts = reinterpret_cast<int32_t*>(wsb + w.off_counts);
 
-    VQB_CUDA_TRY(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), s));
+    VQB_CUDA_TRY(cudaMemsetAsync(counts, 0, 64 + sizeof(int32_t) * kPrunedStateInts, s));
     const int Dpad = L.Dpad;
     if (!presplit) {  // (presplit: the producer of z -- vqb_conv1x1_split_f32 -- already filled z16 / inv / znorm / zres)
         const unsigned blocks = (unsigned)((N + 31) / 32);
@@ -912,61 +945,37 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
             return VQB_ERR_UNSUPPORTED;
     }
     if (rc != VQB_OK) return rc;
-    // exact fp32 choice among the 4 (or 8) certified candidates of every token
-    {
-        const unsigned blocks = (unsigned)((N + 31) / 32);
-#define VQB_RESCORE_G(nch, ex, g)                                                                                       \
-    do {                                                                                                                \
-        constexpr int kSm = (nch) * 32 * 36 * (int)sizeof(float);                                                       \
-        if (kSm > 48 * 1024)                                                                                            \
-            VQB_CUDA_TRY(cudaFuncSetAttribute(rescore_groups_kernel<nch, ex, g>,                                        \
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));                       \
-        rescore_groups_kernel<nch, ex, g><<<blocks, 256, kSm, s>>>(z, E, p.half_norm, p.group1, p.group2, p.group3, N,   \
-                                                                   D, HW, K, idx_out, dmin_out);                        \
-    } while (0)
-#ifdef VQB_EXPERIMENTAL
-    constexpr int kWideNch = 8;
-#else
-    constexpr int kWideNch = kTc16WideGroupDpad / 32;
-#endif
-#define VQB_RESCORE(nch)                                                                                                \
-    do {                                                                                                                \
-        if constexpr ((nch) <= kWideNch) {                                                                              \
-            if (gs == 8) {                                                                                              \
-                if (D == 32 * (nch)) VQB_RESCORE_G(nch, true, 8); else VQB_RESCORE_G(nch, false, 8);                    \
-                break;                                                                                                  \
-            }                                                                                                           \
-        }                                                                                                               \
-        if (D == 32 * (nch)) VQB_RESCORE_G(nch, true, 4); else VQB_RESCORE_G(nch, false, 4);                            \
-    } while (0)
-        switch ((D + 31) / 32) {
-            case 1: VQB_RESCORE(1); break;
-            case 2: VQB_RESCORE(2); break;
-            case 3: VQB_RESCORE(3); break;
-            case 4: VQB_RESCORE(4); break;
-            case 5: VQB_RESCORE(5); break;
-            case 6: VQB_RESCORE(6); break;
-            case 7: VQB_RESCORE(7); break;
-            case 8: VQB_RESCORE(8); break;
-            case 9: VQB_RESCORE(9); break;
-            case 10: VQB_RESCORE(10); break;
-            case 11: VQB_RESCORE(11); break;
-            case 12: VQB_RESCORE(12); break;
-            case 13: VQB_RESCORE(13); break;
-            case 14: VQB_RESCORE(14); break;
-            case 15: VQB_RESCORE(15); break;
-            default: VQB_RESCORE(16); break;
-        }
+    // exact fp32 choice among the 4 (or 8) certified candidates of every token; its score is also the upper bound the
+    // pruned exact tier starts from, so it is kept in the workspace when the caller does not ask for it
+    const bool pruned = g_tc16_pruned && w.pruned_bytes > 0;
+    float* dmin_eff = dmin_out;
+    if (pruned && !dmin_eff) dmin_eff = search_pruned_ubound(wsb + w.off_pruned, N, K, D);
+    switch ((D + 31) / 32) {
+#define VQB_RESCORE(nch) case nch: rc = launch_rescore<nch>(z, E, p, N, D, HW, K, idx_out, dmin_eff, gs, s); break
+        VQB_RESCORE(1); VQB_RESCORE(2); VQB_RESCORE(3); VQB_RESCORE(4); VQB_RESCORE(5); VQB_RESCORE(6); VQB_RESCORE(7);
+        VQB_RESCORE(8); VQB_RESCORE(9); VQB_RESCORE(10); VQB_RESCORE(11); VQB_RESCORE(12); VQB_RESCORE(13); VQB_RESCORE(14);
+        VQB_RESCORE(15);
 #undef VQB_RESCORE
-#undef VQB_RESCORE_G
+        default: rc = launch_rescore<16>(z, E, p, N, D, HW, K, idx_out, dmin_eff, gs, s); break;
     }
+    if (rc != VQB_OK) return rc;
     VQB_LAUNCH_CHECK("rescore_groups_kernel");
-    // ambiguous tokens: full exact fp32 search
-    rc = launch_search_fp32(z, B, D, HW, E, K, pack, p.full_list, p.full_count, N, wsb + w.off_keys, w.keys_bytes,
+    // ambiguous tokens: a LONG list (collapsed codebooks) first meets the pruned exact tier, which either takes all of
+    // it or declines; what is left goes to the full exact fp32 search
+    const int32_t* remaining = p.full_count;
+    const int32_t* handled = nullptr;
+    if (pruned) {
+        rc = launch_search_pruned(z, B, D, HW, E, K, pack, p.full_list, p.full_count, dmin_eff,
+                                  reinterpret_cast<unsigned long long*>(wsb + w.off_keys), counts + 16, wsb + w.off_pruned,
+                                  w.pruned_bytes,
+                                  idx_out, dmin_out, &remaining, &handled, s);
+        if (rc != VQB_OK) return rc;
+    }
+    rc = launch_search_fp32(z, B, D, HW, E, K, pack, p.full_list, remaining, N, wsb + w.off_keys, w.keys_bytes,
                             idx_out, dmin_out, s);
     if (rc != VQB_OK) return rc;
     if (stats_out) {
-        tc16_stats_kernel<<<1, 1, 0, s>>>(stats_out, p.full_count, p.pair_count);
+        tc16_stats_kernel<<<1, 1, 0, s>>>(stats_out, p.full_count, p.pair_count, handled);
         VQB_LAUNCH_CHECK("tc16_stats_kernel");
     }
     return VQB_OK;
