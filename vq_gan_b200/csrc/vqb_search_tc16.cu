@@ -965,10 +965,8 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
     const int32_t* remaining = p.full_count;
     const int32_t* handled = nullptr;
     if (pruned) {
-        rc = launch_search_pruned(z, B, D, HW, E, K, pack, p.full_list, p.full_count, dmin_eff,
-                                  reinterpret_cast<unsigned long long*>(wsb + w.off_keys), counts + 16, wsb + w.off_pruned,
-                                  w.pruned_bytes,
-                                  idx_out, dmin_out, &remaining, &handled, s);
+        rc = launch_search_pruned(z, B, D, HW, E, K, pack, p.full_list, p.full_count, dmin_eff, counts + 16,
+                                  wsb + w.off_pruned, w.pruned_bytes, idx_out, dmin_out, &remaining, &handled, s);
         if (rc != VQB_OK) return rc;
     }
     rc = launch_search_fp32(z, B, D, HW, E, K, pack, p.full_list, remaining, N, wsb + w.off_keys, w.keys_bytes,
