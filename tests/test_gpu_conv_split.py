@@ -52,7 +52,9 @@ def test_fused_conv_split_changes_nothing_downstream(Cin, Cout, K, B, HW):
     assert torch.equal(idx_a, idx_b) and torch.equal(zq_a, zq_b)
     assert ld_a["codebook_loss"] == ld_b["codebook_loss"]
     assert torch.equal(xa.grad, xb.grad) or torch.allclose(ga[0], xb.grad, rtol=1e-6, atol=1e-9)
-    assert torch.allclose(ga[1], conv.weight.grad, rtol=1e-5, atol=1e-8)
+    # dW is a tokens-long reduction whose partial sums meet in atomics (conv1x1_dw_kernel): the order, hence the last bits,
+    # differ from run to run -- tolerance relative to the largest entry, like dE
+    assert torch.allclose(ga[1], conv.weight.grad, rtol=1e-5, atol=1e-5 * float(ga[1].abs().max()))
     assert torch.allclose(ga[2], vq.embedding.weight.grad, rtol=1e-5, atol=1e-9)
     print(f"Cin={Cin} Cout={Cout} K={K}: stats plain {stats_a} fused {stats_b}")
 
