@@ -24,10 +24,10 @@ def _as_images(rows, HW):
 
 @pytest.mark.parametrize("K,D,centres,tokens,HW,expect_tier", [
     (4096, 64, 8, 16384, 1024, True),     # the tier takes every token
-    (2500, 100, 5, 12288, 256, True),     # K not a multiple of the 128-code tiles, D not a multiple of 32
-    (16384, 256, 16, 8192, 1024, True),   # C3's codebook size
-    (4096, 64, 1, 8192, 1024, False),     # ONE centre: every tile survives for every token, the tier declines
-    (4096, 64, 8, 2048, 1024, False),     # a short list stays with the plain list search
+    (2500, 100, 5, 16384, 256, True),     # K not a multiple of the 128-code tiles, D not a multiple of 32
+    (16384, 256, 16, 16384, 1024, True),  # C3's codebook size
+    (4096, 64, 1, 16384, 1024, False),    # ONE centre: every tile survives for every token, the tier declines
+    (4096, 64, 8, 8192, 1024, False),     # a small batch (< 16384 tokens) stays with the plain list search
 ])
 def test_collapsed_codebook_equals_the_fp32_search(K, D, centres, tokens, HW, expect_tier):
     from vq_gan_b200 import ops
@@ -49,7 +49,7 @@ def test_exact_duplicates_keep_the_lowest_index():
     g = torch.Generator().manual_seed(2)
     centres = torch.randn(6, 64, generator=g)
     E = centres[torch.randint(0, 6, (4096,), generator=g)].contiguous()
-    z = centres[torch.randint(0, 6, (8192,), generator=g)] + 0.05 * torch.randn(8192, 64, generator=g)
+    z = centres[torch.randint(0, 6, (16384,), generator=g)] + 0.05 * torch.randn(16384, 64, generator=g)
     zc, Ec = _as_images(z, 1024).cuda(), E.cuda()
     idx, dmin, st = ops.search(zc, Ec, 4)
     ref_idx, ref_dmin, _ = ops.search(zc, Ec, 2)

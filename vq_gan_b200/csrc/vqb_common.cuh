@@ -213,6 +213,7 @@ int launch_search_pruned(const float* z, int64_t B, int D, int64_t HW, const flo
                          const int32_t* token_list, const int32_t* list_count, const float* ubound, int32_t* state,
                          void* ws, size_t ws_bytes, int64_t* idx_out, float* dmin_out, const int32_t** remaining,
                          const int32_t** handled, cudaStream_t s);
+constexpr int64_t kPrunedMinBatch = 16384;  // tokens per search call below which the tier is not even launched
 constexpr int kPrunedStateInts = 16 + 2 * 128;  // zeroed by the caller: decision / counters, per-tile counts, cursors
 size_t search_tc16_workspace_bytes(int64_t n_tokens, int D, int K);
 int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float* E, int K,

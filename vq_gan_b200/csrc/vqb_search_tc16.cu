@@ -947,7 +947,9 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
     if (rc != VQB_OK) return rc;
     // exact fp32 choice among the 4 (or 8) certified candidates of every token; its score is also the upper bound the
     // pruned exact tier starts from, so it is kept in the workspace when the caller does not ask for it
-    const bool pruned = g_tc16_pruned && w.pruned_bytes > 0;
+    // (idle cost: five launches that return at once, ~18 us per search -- 0.2 % at C3, 1 % of a 458 K-token C5 step;
+    // below kPrunedMinBatch tokens even the worst case of the full re-search is a few milliseconds, so the tier is left out)
+    const bool pruned = g_tc16_pruned && w.pruned_bytes > 0 && N >= kPrunedMinBatch;
     float* dmin_eff = dmin_out;
     if (pruned && !dmin_eff) dmin_eff = search_pruned_ubound(wsb + w.off_pruned, N, K, D);
     switch ((D + 31) / 32) {
