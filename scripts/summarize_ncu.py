@@ -27,6 +27,10 @@ KEYS = [
     "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_tensor.sum",
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
