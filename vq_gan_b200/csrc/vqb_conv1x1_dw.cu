@@ -12,6 +12,9 @@
 // the (chunk, tile) pairs; 128 x 256 x 8 MMAs read 12 KB of operands per 128 tensor cycles, 128 x 128 x 8 ones the SM's
 // whole 128 B/clk -- shared-memory bandwidth is what bounds this kernel), then adds its partial product to dW with
 // 16-byte reductions (up to 148 partial sums per element: order-dependent in the last bits, like dE).
+// Two experiments that did NOT help (1 M tokens, 256 -> 256, 0.79 ms as it stands): issuing the hi x hi products as soon as
+// TMA lands, before the converters finish (0.80 ms: the conversion is not what the tensor pipe waits for), and a ring of
+// three landed tiles with ONE residual slot (0.98 ms: conversion and residual products then serialise on that slot).
 #include "vqb_tc_common.cuh"
 
 namespace vqb {
