@@ -57,6 +57,11 @@ base = torch.randn(4096, 256, generator=g)
 E = base.repeat_interleave(4, dim=0)[torch.randperm(16384, generator=g)] + 1e-5 * torch.randn(16384, 256, generator=g)
 z = torch.randn(n, 256, generator=g)
 ok &= run("every code duplicated 4x", z, E)
+# the same with EXACT copies (a codebook restarted by copying): the prepare pass hides the later copies, the tokens certify
+Ex = base.repeat_interleave(4, dim=0)[torch.randperm(16384, generator=g)].contiguous()
+ok &= run("every code copied 4x exactly", z, Ex)
+Ex = base[:256].repeat_interleave(64, dim=0)[torch.randperm(16384, generator=g)].contiguous()
+ok &= run("256 distinct codes copied 64x exactly", z, Ex)
 z = torch.randn(n, 256, generator=g)
 z[::97] = float("nan")
 z[5::1013] = float("inf")

@@ -44,7 +44,8 @@ def test_collapsed_codebook_equals_the_fp32_search(K, D, centres, tokens, HW, ex
 
 
 def test_exact_duplicates_keep_the_lowest_index():
-    """Whole clusters of IDENTICAL codes: every score ties exactly, the original (unsorted) index decides."""
+    """Whole clusters of IDENTICAL codes: every score ties exactly, the original (unsorted) index decides.  The prepare
+    pass hides the later copies from the tensor pass (codebook_shadow_kernel), so the tokens certify again."""
     from vq_gan_b200 import ops
     g = torch.Generator().manual_seed(2)
     centres = torch.randn(6, 64, generator=g)
@@ -53,11 +54,33 @@ def test_exact_duplicates_keep_the_lowest_index():
     zc, Ec = _as_images(z, 1024).cuda(), E.cuda()
     idx, dmin, st = ops.search(zc, Ec, 4)
     ref_idx, ref_dmin, _ = ops.search(zc, Ec, 2)
-    assert st.tolist()[3] == st.tolist()[0] > 0
-    assert torch.equal(idx, ref_idx) and torch.equal(dmin, ref_dmin)
+    assert st.tolist()[0] < 0.01 * 16384, st.tolist()   # (before the shadowing: every token uncertified)
+    # certified tokens get their score from the candidate re-score (another, equally exact fp32 summation order)
+    assert torch.equal(idx, ref_idx) and torch.allclose(dmin, ref_dmin, rtol=1e-5, atol=1e-4)
     # the winner is the FIRST code of the token's cluster
     first = torch.stack([(E == E[i]).all(dim=1).nonzero()[0, 0] for i in ref_idx.reshape(-1)[:64].cpu()])
     assert torch.equal(first, ref_idx.reshape(-1)[:64].cpu())
+
+
+@pytest.mark.parametrize("copies,D", [(4, 64), (8, 256), (64, 128)])
+def test_codebook_of_exact_copies_certifies(copies, D):
+    """A healthy codebook restarted by COPYING codes (every distinct code `copies` times, shuffled): four or more equal
+    scores used to fill every candidate slot of the tensor pass and send each token to the exact full search."""
+    from vq_gan_b200 import ops
+    g = torch.Generator().manual_seed(copies + D)
+    K = 8192
+    base = torch.randn(K // copies, D, generator=g)
+    E = base.repeat_interleave(copies, dim=0)[torch.randperm(K, generator=g)].contiguous()
+    z = torch.randn(16384, D, generator=g)
+    zc, Ec = _as_images(z, 1024).cuda(), E.cuda()
+    idx, dmin, st = ops.search(zc, Ec, 4)
+    ref_idx, ref_dmin, _ = ops.search(zc, Ec, 2)
+    assert st.tolist()[0] < 0.01 * 16384, st.tolist()
+    assert torch.equal(idx, ref_idx) and torch.allclose(dmin, ref_dmin, rtol=1e-5, atol=1e-4)
+    # every winner is the first of its copies
+    rows = E[ref_idx.reshape(-1)[:32].cpu()]
+    first = torch.stack([(E == r).all(dim=1).nonzero()[0, 0] for r in rows])
+    assert torch.equal(first, ref_idx.reshape(-1)[:32].cpu())
 
 
 def test_nan_and_inf_tokens_and_module_forward():

@@ -64,6 +64,10 @@ int sm_count();      // SM count of the current device (valid after device_ready
 // ehi, elo : bf16[Kpad][D]      (tensor path) E ~= ehi + elo, zero rows for k >= K
 // e16      : fp16[Kpad][Dpad]   (single-pass tensor path, 16 < D <= 256) fp16(E * 2^se), zero rows for k >= K,
 //            zero columns for d >= D (Dpad = D rounded up to 64)
+// half_norm_fin: like half_norm with a large FINITE pad (1e38), read by the tensor kernel's key-packing epilogue; a code
+//            whose row is bit-identical to that of a LOWER-indexed code is padded too (it can never be the answer:
+//            ties go to the lowest index), so that a codebook full of copies does not fill every candidate slot with
+//            the same score.  rowhash / dup: the hash table that finds them (codebook_shadow_kernel)
 constexpr int kPadCodes = 256;
 constexpr int kHeaderBytes = 256;
 constexpr int kLowDMax = 16;
@@ -84,9 +88,11 @@ __host__ __device__ inline int tc16_dpad(int D) { return round_up_i(D, 64); }
 
 struct PackLayout {
     int K, D, Kpad;
-    size_t off_half_norm, off_pairs, off_ehi, off_elo, off_e16, off_half_norm_fin, off_img, off_gmax, off_cmax, total;
+    size_t off_half_norm, off_pairs, off_ehi, off_elo, off_e16, off_half_norm_fin, off_img, off_gmax, off_cmax, off_rowhash,
+        off_dup, total;
     bool has_pairs, has_bf16, has_e16;
-    int Dpad;  // row length of the fp16 image (D rounded up to 64)
+    int Dpad;       // row length of the fp16 image (D rounded up to 64)
+    int dup_slots;  // power of two >= 2 Kpad: open-addressing table of (row hash << 32 | lowest code index) words
 };
 
 // ---- tf32x3 operand images of the low-D tensor path (vqb_search_tclow.cu) -----------------
@@ -131,6 +137,13 @@ __host__ __device__ inline PackLayout pack_layout(int K, int D) {
     if (L.has_e16) off = round_up_z(off + sizeof(float) * (L.Kpad / 4), 1024);
     L.off_cmax = off;
     if (L.has_pairs) off = round_up_z(off + sizeof(float) * (L.Kpad / 32), 1024);
+    // exact-duplicate detection (fp16 tensor path): later copies of a code are hidden from the approximate pass
+    L.dup_slots = 1;
+    while (L.dup_slots < 2 * L.Kpad) L.dup_slots <<= 1;
+    L.off_rowhash = off;
+    if (L.has_e16) off = round_up_z(off + 4 * (size_t)L.Kpad, 1024);
+    L.off_dup = off;
+    if (L.has_e16) off = round_up_z(off + 8 * (size_t)L.dup_slots, 1024);
     L.total = off;
     return L;
 }

@@ -60,9 +60,18 @@ __global__ void __launch_bounds__(256) codebook_prepare_kernel(const float* __re
 
     float sq = 0.f, res = 0.f;
     bool bad = false;
+    uint32_t hsum = 0u;  // order-independent row hash: sum over d of mix(bits(v_d), d)
     for (int d = lane; d < D; d += 32) {
         const float v = live ? E[(size_t)k * D + d] : 0.f;
         sq = fmaf(v, v, sq);
+        if (L.has_e16) {
+            uint32_t x = __float_as_uint(v) ^ ((uint32_t)d * 0x9E3779B9u);
+            x *= 0x85EBCA6Bu;
+            x ^= x >> 13;
+            x *= 0xC2B2AE35u;
+            x ^= x >> 16;
+            hsum += x;
+        }
         bad |= (v != v);
         if (L.has_pairs) {
             // pair p = k/2 holds e_d(2p), e_d(2p+1) adjacent for every d
@@ -88,7 +97,29 @@ __global__ void __launch_bounds__(256) codebook_prepare_kernel(const float* __re
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
     bad = __any_sync(0xffffffffu, bad);
+    if (L.has_e16) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
+    }
     if (lane == 0) {
+        if (L.has_e16) {
+            reinterpret_cast<uint32_t*>(pack + L.off_rowhash)[k] = hsum;
+            if (live) {
+                // first-fit open addressing, no deletions: every row with this hash ends up in the same slot, which keeps
+                // the LOWEST code index among them (hash in the high word, so a 64-bit min orders equal hashes by index)
+                unsigned long long* table = reinterpret_cast<unsigned long long*>(pack + L.off_dup);
+                const unsigned long long key = ((unsigned long long)hsum << 32) | (unsigned)k;
+                for (int pr = 0; pr < 64; ++pr) {
+                    unsigned long long* slot = table + ((hsum + (uint32_t)pr) & (uint32_t)(L.dup_slots - 1));
+                    const unsigned long long old = atomicCAS(slot, ~0ull, key);
+                    if (old == ~0ull) break;
+                    if ((uint32_t)(old >> 32) == hsum) {
+                        atomicMin(slot, key);
+                        break;
+                    }
+                }
+            }
+        }
         half_norm[k] = live ? 0.5f * sq : INFINITY;
         if (L.has_e16) {
             const float h = 0.5f * sq;
@@ -110,6 +141,34 @@ __global__ void __launch_bounds__(256) codebook_prepare_kernel(const float* __re
             }
         }
     }
+}
+
+// Hides every code whose row is bit-identical to that of a lower-indexed code from the fp16 tensor pass (half_norm_fin
+// -> the finite pad): such a code can never be the answer (lowest index wins ties), but FOUR or more copies of a popular
+// code -- a codebook restarted by copying live codes onto dead ones -- would occupy all four candidate slots of the
+// epilogue with the same score and send every token near it to the exact full search.  The exact tiers read half_norm,
+// which is untouched.  One thread per code; the row comparison only runs for hash matches.
+__global__ void __launch_bounds__(256) codebook_shadow_kernel(const float* __restrict__ E, int K, int D, unsigned char* pack,
+                                                              PackLayout L) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const uint32_t h = reinterpret_cast<const uint32_t*>(pack + L.off_rowhash)[k];
+    const unsigned long long* table = reinterpret_cast<const unsigned long long*>(pack + L.off_dup);
+    int k0 = k;
+    for (int pr = 0; pr < 64; ++pr) {
+        const unsigned long long e = table[(h + (uint32_t)pr) & (uint32_t)(L.dup_slots - 1)];
+        if (e == ~0ull) break;
+        if ((uint32_t)(e >> 32) == h) {
+            k0 = (int)(uint32_t)(e & 0xffffffffull);
+            break;
+        }
+    }
+    if (k0 >= k) return;
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(E + (size_t)k0 * D);
+    const uint32_t* b = reinterpret_cast<const uint32_t*>(E + (size_t)k * D);
+    for (int d = 0; d < D; ++d)
+        if (a[d] != b[d]) return;
+    reinterpret_cast<float*>(pack + L.off_half_norm_fin)[k] = 1e38f;
 }
 
 // tf32x3 image of the codebook for the low-D tensor path: one thread per (padded) code row.
@@ -171,14 +230,20 @@ int launch_codebook_prepare(const float* E, int K, int D, void* pack, cudaStream
         codebook_absmax_kernel<<<(unsigned)ab, 256, 0, s>>>(E, n, reinterpret_cast<int*>(pack));
         VQB_LAUNCH_CHECK("codebook_absmax_kernel");
     }
-    if (L.has_e16)
+    if (L.has_e16) {
         VQB_CUDA_TRY(cudaMemsetAsync(static_cast<unsigned char*>(pack) + L.off_gmax, 0, sizeof(float) * (L.Kpad / 4), s));
+        VQB_CUDA_TRY(cudaMemsetAsync(static_cast<unsigned char*>(pack) + L.off_dup, 0xff, 8 * (size_t)L.dup_slots, s));
+    }
     if (L.has_pairs)
         VQB_CUDA_TRY(cudaMemsetAsync(static_cast<unsigned char*>(pack) + L.off_cmax, 0, sizeof(float) * (L.Kpad / 32), s));
     const int warps = 8;
     const int blocks = (L.Kpad + warps - 1) / warps;
     codebook_prepare_kernel<<<blocks, warps * 32, 0, s>>>(E, K, D, static_cast<unsigned char*>(pack), L);
     VQB_LAUNCH_CHECK("codebook_prepare_kernel");
+    if (L.has_e16) {
+        codebook_shadow_kernel<<<(K + 255) / 256, 256, 0, s>>>(E, K, D, static_cast<unsigned char*>(pack), L);
+        VQB_LAUNCH_CHECK("codebook_shadow_kernel");
+    }
     if (L.has_pairs) {
         codebook_image_kernel<<<(L.Kpad + 127) / 128, 128, 0, s>>>(E, K, D, static_cast<unsigned char*>(pack), L);
         VQB_LAUNCH_CHECK("codebook_image_kernel");
