@@ -59,7 +59,8 @@ def make_codebook(kind, K, D, device=None, tokens=None):
     """normal: N(0,1) seed 1 (SURVEY 8d primary).  refinit: the reference constructor's U(+-1/K)
     (quantizer.py:48) under torch.manual_seed(42).  trained: K distinct tokens + 0.01 N(0,1) (SURVEY 8d C1
     variant).  clustered: 16 centres, codes 1e-4 apart (collapsed codebook, adversarial for any low-precision
-    first pass)."""
+    first pass).  copied: K/4 N(0,1) codes, each present four times bit for bit, shuffled (a codebook restarted by copying
+    live codes onto dead ones)."""
     if kind == "normal":
         E = torch.randn(K, D, generator=torch.Generator().manual_seed(1))
     elif kind == "refinit":
@@ -73,6 +74,13 @@ def make_codebook(kind, K, D, device=None, tokens=None):
         rows = tokens.permute(0, 2, 3, 1).reshape(-1, D)
         pick = torch.randperm(rows.shape[0], generator=torch.Generator().manual_seed(1))[:K].to(rows.device)
         E = rows[pick].cpu() + 0.01 * torch.randn(K, D, generator=torch.Generator().manual_seed(11))
+    elif kind == "copied":
+        g = torch.Generator().manual_seed(1)
+        base = torch.randn(max(K // 4, 1), D, generator=g)
+        E = base.repeat_interleave(4, dim=0)[:K]
+        if E.shape[0] < K:
+            E = torch.cat([E, torch.randn(K - E.shape[0], D, generator=g)])
+        E = E[torch.randperm(K, generator=g)]
     elif kind == "clustered":
         g = torch.Generator().manual_seed(1)
         centres = torch.randn(16, D, generator=g)
@@ -961,7 +969,7 @@ def measure_quantizer(args, workload, world, rank, local_rank, device, peaks, fm
     return line
 
 
-def measure_codebook_variants(args, workload, world, rank, device, kinds=("refinit", "trained", "clustered")):
+def measure_codebook_variants(args, workload, world, rank, device, kinds=("refinit", "trained", "copied", "clustered")):
     """Search-only timing of `workload` on the secondary codebooks of SURVEY 8(d) and on a collapsed one:
     how many tokens fall through the certified tensor pass to the exact tiers, and what that costs."""
     from vq_gan_b200 import ops
@@ -1082,7 +1090,7 @@ def main():
     ap.add_argument("--workload", default="all", choices=sorted(WORKLOADS) + ["all", "c4full"],
                     help="all (default): c2 on top + c3 block (+ c5 block on > 1 GPU); c4full: the reference VQVAE "
                          "training step with the drop-in under DDP")
-    ap.add_argument("--codebook", default="normal", choices=["normal", "refinit", "trained", "clustered"],
+    ap.add_argument("--codebook", default="normal", choices=["normal", "refinit", "trained", "copied", "clustered"],
                     help="codebook law of the quantizer workloads (SURVEY 8d: normal is primary)")
     ap.add_argument("--variants", action="store_true", help="single c2/c3 run: also time the secondary codebooks")
     ap.add_argument("--no-strawman", action="store_true")

@@ -6,8 +6,18 @@
 
 namespace vqb {
 
-__global__ void prepare_header_kernel(int* header, int K, int D) {
-    if (threadIdx.x == 0) {
+// header + everything the later kernels accumulate into with atomics (one launch instead of a kernel and three memsets):
+// the per-group / per-chunk norm maxima (zeros) and the duplicate-detection table (all ones = empty)
+__global__ void __launch_bounds__(256) prepare_header_kernel(int* header, int K, int D, unsigned char* pack, PackLayout L) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    if (L.has_e16)
+        for (size_t i = tid; i < (size_t)L.Kpad / 4; i += nth) reinterpret_cast<float*>(pack + L.off_gmax)[i] = 0.f;
+    if (L.has_pairs)
+        for (size_t i = tid; i < (size_t)L.Kpad / 32; i += nth) reinterpret_cast<float*>(pack + L.off_cmax)[i] = 0.f;
+    if (L.has_e16)
+        for (size_t i = tid; i < (size_t)L.dup_slots / 2; i += nth)
+            reinterpret_cast<ulonglong2*>(pack + L.off_dup)[i] = make_ulonglong2(~0ull, ~0ull);
+    if (tid == 0) {
         header[0] = K;  // first NaN code (atomicMin below)
         header[1] = K;
         header[2] = D;
@@ -148,10 +158,8 @@ __global__ void __launch_bounds__(256) codebook_prepare_kernel(const float* __re
 // code -- a codebook restarted by copying live codes onto dead ones -- would occupy all four candidate slots of the
 // epilogue with the same score and send every token near it to the exact full search.  The exact tiers read half_norm,
 // which is untouched.  One thread per code; the row comparison only runs for hash matches.
-__global__ void __launch_bounds__(256) codebook_shadow_kernel(const float* __restrict__ E, int K, int D, unsigned char* pack,
-                                                              PackLayout L) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= K) return;
+__device__ __forceinline__ bool code_is_shadowed(const float* __restrict__ E, int k, int D, const unsigned char* pack,
+                                                 const PackLayout& L) {
     const uint32_t h = reinterpret_cast<const uint32_t*>(pack + L.off_rowhash)[k];
     const unsigned long long* table = reinterpret_cast<const unsigned long long*>(pack + L.off_dup);
     int k0 = k;
@@ -163,12 +171,19 @@ __global__ void __launch_bounds__(256) codebook_shadow_kernel(const float* __res
             break;
         }
     }
-    if (k0 >= k) return;
+    if (k0 >= k) return false;
     const uint32_t* a = reinterpret_cast<const uint32_t*>(E + (size_t)k0 * D);
     const uint32_t* b = reinterpret_cast<const uint32_t*>(E + (size_t)k * D);
     for (int d = 0; d < D; ++d)
-        if (a[d] != b[d]) return;
-    reinterpret_cast<float*>(pack + L.off_half_norm_fin)[k] = 1e38f;
+        if (a[d] != b[d]) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) codebook_shadow_kernel(const float* __restrict__ E, int K, int D, unsigned char* pack,
+                                                              PackLayout L) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    if (code_is_shadowed(E, k, D, pack, L)) reinterpret_cast<float*>(pack + L.off_half_norm_fin)[k] = 1e38f;
 }
 
 // tf32x3 image of the codebook for the low-D tensor path: one thread per (padded) code row.
@@ -221,8 +236,12 @@ __global__ void __launch_bounds__(128) codebook_image_kernel(const float* __rest
 
 int launch_codebook_prepare(const float* E, int K, int D, void* pack, cudaStream_t s) {
     const PackLayout L = pack_layout(K, D);
-    prepare_header_kernel<<<1, 32, 0, s>>>(reinterpret_cast<int*>(pack), K, D);
-    VQB_LAUNCH_CHECK("prepare_header_kernel");
+    {
+        const size_t words = L.has_e16 ? (size_t)L.dup_slots / 2 : 1;
+        const unsigned hb = (unsigned)((words + 255) / 256 < 64 ? (words + 255) / 256 : 64);
+        prepare_header_kernel<<<hb ? hb : 1, 256, 0, s>>>(reinterpret_cast<int*>(pack), K, D, static_cast<unsigned char*>(pack), L);
+        VQB_LAUNCH_CHECK("prepare_header_kernel");
+    }
     if (L.has_e16) {
         const size_t n = (size_t)K * D;
         size_t ab = (n + 255) / 256;
@@ -230,12 +249,6 @@ int launch_codebook_prepare(const float* E, int K, int D, void* pack, cudaStream
         codebook_absmax_kernel<<<(unsigned)ab, 256, 0, s>>>(E, n, reinterpret_cast<int*>(pack));
         VQB_LAUNCH_CHECK("codebook_absmax_kernel");
     }
-    if (L.has_e16) {
-        VQB_CUDA_TRY(cudaMemsetAsync(static_cast<unsigned char*>(pack) + L.off_gmax, 0, sizeof(float) * (L.Kpad / 4), s));
-        VQB_CUDA_TRY(cudaMemsetAsync(static_cast<unsigned char*>(pack) + L.off_dup, 0xff, 8 * (size_t)L.dup_slots, s));
-    }
-    if (L.has_pairs)
-        VQB_CUDA_TRY(cudaMemsetAsync(static_cast<unsigned char*>(pack) + L.off_cmax, 0, sizeof(float) * (L.Kpad / 32), s));
     const int warps = 8;
     const int blocks = (L.Kpad + warps - 1) / warps;
     codebook_prepare_kernel<<<blocks, warps * 32, 0, s>>>(E, K, D, static_cast<unsigned char*>(pack), L);
