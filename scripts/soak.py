@@ -140,5 +140,30 @@ for case in range(n_cases):
         if not (e_y < 2e-5 and e_dx < 1e-4 and e_dw < 1e-4 and e_db < 1e-4):
             print(f"FAIL case {case} groupnorm B={B} C={C} G={G} HW={hw}: y {e_y:.2e} dx {e_dx:.2e} dw {e_dw:.2e} db {e_db:.2e}", flush=True)
             fails += 1
+# collapsed codebooks (pruned exact tier of the fp16 tensor search): identical to the fp32 tile kernel, indices and scores
+n_collapsed = max(n_cases // 12, 4)
+taken = 0
+for case in range(n_collapsed):
+    D = int(rng.choice([17, 33, 64, 100, 192, 256, 320, 512]))
+    K = int(rng.choice([2048, 2500, 4096, 9000, 16384]))
+    nc = int(rng.choice([2, 5, 16, 40]))
+    seed = int(rng.integers(0, 1 << 30))
+    g = torch.Generator().manual_seed(seed)
+    centres = torch.randn(nc, D, generator=g) * float(rng.choice([1.0, 1e-2, 30.0]))
+    spread = float(rng.choice([0.0, 1e-5, 1e-4])) * float(centres.abs().max())
+    E = centres[torch.randint(0, nc, (K,), generator=g)] + spread * torch.randn(K, D, generator=g)
+    z = centres[torch.randint(0, nc, (16384,), generator=g)] + 0.05 * float(centres.abs().max()) * torch.randn(16384, D, generator=g)
+    zc = z.view(16, 1024, D).permute(0, 2, 1).contiguous().cuda()
+    i4, d4, st = ops.search(zc, E.cuda(), 4)
+    i2, d2, _ = ops.search(zc, E.cuda(), 2)
+    st = st.tolist()
+    taken += int(st[3] > 0)
+    certified = st[0] < 16384 // 2
+    same_d = torch.equal(d4, d2) if not certified else torch.allclose(d4, d2, rtol=1e-5, atol=1e-5 * float(d2.abs().max()))
+    if not (torch.equal(i4, i2) and same_d):
+        print(f"FAIL collapsed case {case} D={D} K={K} centres={nc} spread={spread:.2e} seed={seed}: stats={st} "
+              f"idx mismatches {(i4 != i2).sum().item()}", flush=True)
+        fails += 1
+print(f"soak: collapsed codebooks {n_collapsed} cases, pruned tier took the list in {taken}")
 print(f"soak: {n_cases} cases, {fails} failures, {time.time() - t_start:.1f} s")
 sys.exit(1 if fails else 0)
