@@ -1009,6 +1009,88 @@ def measure_codebook_variants(args, workload, world, rank, device, kinds=("refin
     return out
 
 
+def measure_next_rows(device, peaks):
+    """Rows N1 / N2 of SURVEY 8(f) in the driver-run line: the 1x1 convolution either side of the quantizer (forward and
+    parameter gradients) and the GroupNorm+SiLU in front of `conv_out`, each timed with CUDA events on inputs larger than
+    L2, as a fraction of the HBM peak for its algorithmic bytes, next to the stock torch op, with a parity self-check."""
+    import torch.nn.functional as F
+    from vq_gan_b200 import ops
+
+    def timed(fn, n=8):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / n
+
+    hbm = peaks["hbm_gbs"]
+    out = {"note": "builder-side extras of the same line; inputs 0.5-1 GB each (> 126 MB L2); frac = algorithmic bytes / time / "
+                   f"{hbm:.0f} GB/s"}
+    g = torch.Generator(device=device).manual_seed(7)
+    B, C, H, W = 512, 256, 32, 32
+    tokens = B * H * W
+    x = torch.randn(B, C, H, W, device=device, generator=g)
+    gy = torch.randn(B, C, H, W, device=device, generator=g)
+    wt = torch.randn(C, C, device=device, generator=g) / C ** 0.5
+    bs = torch.randn(C, device=device, generator=g)
+    t_f = timed(lambda: ops.conv1x1(x, wt, bs))
+    t_w = timed(lambda: ops.conv1x1_param_grads(gy, x))
+    conv = torch.nn.Conv2d(C, C, 1).to(device)
+    t_f_ref = timed(lambda: conv(x))
+    t_w_ref = timed(lambda: (torch.einsum("bot,bct->oc", gy.reshape(B, C, -1), x.reshape(B, C, -1)), gy.sum(dim=(0, 2, 3))))
+    nb = 4.0 * tokens * 2 * C
+    y = ops.conv1x1(x[:8], wt, bs)
+    ref = torch.einsum("oc,bchw->bohw", wt.double(), x[:8].double()) + bs.double().view(1, -1, 1, 1)
+    bound = torch.einsum("oc,bchw->bohw", wt.abs().double(), x[:8].abs().double()) + bs.abs().double().view(1, -1, 1, 1)
+    e_f = float(((y.double() - ref).abs() / bound).max())
+    gw, gb = ops.conv1x1_param_grads(gy[:32], x[:32])
+    wref = torch.einsum("bot,bct->oc", gy[:32].double().reshape(32, C, -1), x[:32].double().reshape(32, C, -1))
+    wbound = torch.einsum("bot,bct->oc", gy[:32].double().abs().reshape(32, C, -1), x[:32].double().abs().reshape(32, C, -1))
+    e_w = float(((gw.double() - wref).abs() / wbound).max())
+    out["n1_conv1x1_256_to_256"] = {
+        "tokens": tokens,
+        "forward": {"kernel": "conv1x1_tc_kernel", "ms": t_f, "frac_hbm": nb / (t_f * 1e-3) / 1e9 / hbm,
+                    "tflops_executed_tf32": 6.0 * tokens * C * C / (t_f * 1e-3) / 1e12, "torch_cudnn_tf32_ms": t_f_ref,
+                    "max_err_over_bound": e_f},
+        "param_grads": {"kernel": "conv1x1_dw_kernel", "ms": t_w, "frac_hbm": nb / (t_w * 1e-3) / 1e9 / hbm,
+                        "tflops_executed_tf32": 6.0 * tokens * C * C / (t_w * 1e-3) / 1e12, "torch_fp32_gemm_ms": t_w_ref,
+                        "max_err_over_bound": e_w},
+        "parity_check": "ok" if (e_f < 3e-6 and e_w < 4e-6) else "FAILED"}
+    del x, gy, y, ref, bound, conv
+    torch.cuda.empty_cache()
+    B, C = 512, 512
+    x = torch.randn(B, C, H, W, device=device, generator=g)
+    gy = torch.randn(B, C, H, W, device=device, generator=g)
+    w = 1 + 0.3 * torch.randn(C, device=device, generator=g)
+    b = 0.2 * torch.randn(C, device=device, generator=g)
+    t_f = timed(lambda: ops.groupnorm_silu(x, w, b, 32, 1e-6))
+    y, mean, rstd = ops.groupnorm_silu(x, w, b, 32, 1e-6)
+    t_b = timed(lambda: ops.groupnorm_silu_backward(gy, x, w, b, mean, rstd, 32))
+    t_f_ref = timed(lambda: F.silu(F.group_norm(x, 32, w, b, 1e-6)))
+    xs = x[:4].clone().requires_grad_(True)
+    yr = F.silu(F.group_norm(xs, 32, w, b, 1e-6))
+    yr.backward(gy[:4])
+    dx, _, _ = ops.groupnorm_silu_backward(gy[:4], x[:4], w, b, mean[:4 * 32], rstd[:4 * 32], 32)
+    e_y = float((y[:4] - yr.detach()).abs().max())
+    e_dx = float((dx - xs.grad).abs().max() / xs.grad.abs().max())
+    nbx = 4.0 * x.numel()
+    out["n2_groupnorm_silu_512ch_32x32"] = {
+        "elements": x.numel(),
+        "forward": {"kernel": "groupnorm_silu_fwd_kernel", "ms": t_f, "frac_hbm": 2 * nbx / (t_f * 1e-3) / 1e9 / hbm,
+                    "torch_ms": t_f_ref, "max_abs_err": e_y},
+        "backward": {"kernel": "groupnorm_silu_bwd_reg_kernel", "ms": t_b, "frac_hbm": 3 * nbx / (t_b * 1e-3) / 1e9 / hbm,
+                     "max_rel_err_dx": e_dx},
+        "parity_check": "ok" if (e_y < 2e-5 and e_dx < 1e-4) else "FAILED"}
+    del x, gy, y
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu_arm(args):
     import torch.distributed as dist
     from vq_gan_b200 import ops
@@ -1066,7 +1148,15 @@ def run_gpu_arm(args):
             c4 = run_full_step(args, world, rank, local_rank, device, peaks, steps=3, warmup=2)
         except Exception as e:  # the block is context; it must never take the headline down with it
             c4 = {"workload": "c4full", "failed": f"{type(e).__name__}: {e}"[:300]} if rank == 0 else None
+    nxt = None
+    if world == 1 and not args.no_c4:
+        try:
+            nxt = measure_next_rows(device, peaks)
+        except Exception as e:  # context only, never fatal
+            nxt = {"failed": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
+        if nxt is not None:
+            line["next_rows"] = nxt
         c3["codebooks"] = variants
         line["codebooks"] = variants_c2
         line["c3"] = c3

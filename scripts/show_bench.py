@@ -31,3 +31,5 @@ if d.get("codebooks"):
         print("   c2 codebook", k, v)
 if "c4" in d:
     print("== c4:", json.dumps(d["c4"])[:900])
+if "next_rows" in d:
+    print("== next rows (N1 / N2):", json.dumps(d["next_rows"])[:2000])
