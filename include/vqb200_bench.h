@@ -27,6 +27,8 @@ extern "C" {
  *   "tc16_group"         0|4|8  codes per candidate group of the fp16 tensor search (0 = 8 up to padded D 128, 4 above)
  *   "dw_hw_trunc"        0|1    1x1 conv parameter gradients: 1 = the landed fp32 tile is the hi image as it is (relies on the
  *                               tensor core ignoring the low 13 mantissa bits), only the residual image is written
+ *   "norm_bwd2"          0|1    GroupNorm+SiLU backward (<= 16 items per group): one 512-thread CTA per SM with xhat and dxhat in
+ *                               registers / two per SM with xhat in shared memory (default 1)
  *   "norm_cluster"       0|1|2  GroupNorm+SiLU: round-1 staged kernels only / product (default 1) / also clusters of
  *                               2-8 CTAs per (image, group) (measured slower)
  *   "tclow_cluster"      1|2|4  same for the low-D tensor search

@@ -35,6 +35,14 @@ for B, C, H, W, mode in [(b, c, h, w, m) for (b, c, h, w) in ((64, 512, 32, 32),
     tt = timed(lambda: F.silu(F.group_norm(x, 32, w, b, 1e-6)))
     y, mean, rstd = ops.groupnorm_silu(x, w, b, 32, 1e-6)
     tb = timed(lambda: ops.groupnorm_silu_backward(gy, x, w, b, mean, rstd, 32))
+    if mode == 1:  # A/B of the register-resident backward: one CTA per SM (norm_bwd2 0) vs two (default)
+        d1 = ops.groupnorm_silu_backward(gy, x, w, b, mean, rstd, 32)[0]
+        _cabi.check(lib.vqb_tune(b"norm_bwd2", 0), "t")
+        tb1 = timed(lambda: ops.groupnorm_silu_backward(gy, x, w, b, mean, rstd, 32))
+        d0 = ops.groupnorm_silu_backward(gy, x, w, b, mean, rstd, 32)[0]
+        _cabi.check(lib.vqb_tune(b"norm_bwd2", 1), "t")
+        print(f"[{B},{C},{H},{W}] backward: two CTAs per SM, xhat in shared memory (product) {tb:.3f} ms vs one CTA per SM, all in "
+              f"registers {tb1:.3f} ms; same dx: {torch.equal(d0, d1)}", flush=True)
     xr = x.clone().requires_grad_(True)
 
     def torch_fb():

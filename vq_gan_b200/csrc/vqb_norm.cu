@@ -556,6 +556,103 @@ __global__ void __launch_bounds__(kNormThreads, 1)
     }
 }
 
+// The register-resident backward with TWO CTAs per SM (the product path; vqb_tune "norm_bwd2" 0 selects the one above):
+// xhat goes to shared memory (64 KB per CTA at the encoder tail), only dxhat stays in registers (32 per thread), x and dy
+// are loaded one after the other so that a thread never holds more than eight float4 -- the register budget of 64 that
+// two 512-thread CTAs leave.  One CTA's loads now overlap the other's arithmetic and stores: [1024, 512, 32, 32]
+// 1.52 -> 1.21 ms (0.65 -> 0.82 of the HBM peak for its three passes), bit-identical dx.
+__global__ void __launch_bounds__(kNormThreads, 2)
+    groupnorm_silu_bwd_reg2_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ mean_in,
+                                   const float* __restrict__ rstd_in, int C, int64_t HW, int G, float* __restrict__ dx,
+                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    extern __shared__ __align__(16) float stage[];  // xhat: [warp][8][32 lanes] float4
+    __shared__ float red[kNormThreads / 32];
+    const int cpg = C / G;
+    const int64_t n = (int64_t)cpg * HW;
+    const int64_t bg = blockIdx.x;
+    const int g = (int)(bg % G);
+    const float mean = mean_in[bg], rstd = rstd_in[bg];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t segs = (HW + kNormSeg - 1) / kNormSeg;
+    const int64_t items = (int64_t)cpg * segs;
+    const bool live = warp < items;
+    const int cc = live ? (int)(warp / segs) : 0;
+    const int64_t lo = live ? (warp - (int64_t)cc * segs) * kNormSeg : 0;
+    const int64_t hi = live ? (lo + kNormSeg < HW ? lo + kNormSeg : HW) : 0;
+    const int64_t base = bg * n + (int64_t)cc * HW;
+    const int c = g * cpg + cc;
+    float4* sx = reinterpret_cast<float4*>(stage) + (size_t)warp * 256 + lane;  // [u][lane]: conflict-free
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int64_t i = lo + 4 * lane + 128 * u;
+        v[u] = i < hi ? __ldg(reinterpret_cast<const float4*>(x + base + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        float4 h;
+        h.x = (v[u].x - mean) * rstd;
+        h.y = (v[u].y - mean) * rstd;
+        h.z = (v[u].z - mean) * rstd;
+        h.w = (v[u].w - mean) * rstd;
+        sx[32 * u] = h;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int64_t i = lo + 4 * lane + 128 * u;
+        v[u] = i < hi ? __ldg(reinterpret_cast<const float4*>(dy + base + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float ga = __ldg(gamma + c), be = __ldg(beta + c);
+    float dg = 0.f, db = 0.f, s1 = 0.f, s2 = 0.f;
+    auto one = [&](float xhat, float& dv) {  // dy -> dxhat in place
+        const float u = fmaf(xhat, ga, be);
+        const float sg = 1.f / (1.f + __expf(-u));
+        const float gu = dv * sg * fmaf(u, 1.f - sg, 1.f);
+        dg = fmaf(gu, xhat, dg);
+        db += gu;
+        const float dxh = gu * ga;
+        s1 += dxh;
+        s2 = fmaf(dxh, xhat, s2);
+        dv = dxh;
+    };
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        if (lo + 4 * lane + 128 * u < hi) {
+            const float4 h = sx[32 * u];
+            one(h.x, v[u].x);
+            one(h.y, v[u].y);
+            one(h.z, v[u].z);
+            one(h.w, v[u].w);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dg += __shfl_xor_sync(0xffffffffu, dg, o);
+        db += __shfl_xor_sync(0xffffffffu, db, o);
+    }
+    if (live && lane == 0) {
+        if (dgamma) atomicAdd(dgamma + c, dg);
+        if (dbeta) atomicAdd(dbeta + c, db);
+    }
+    const float inv_n = 1.f / (float)n;
+    const float m1 = block_sum(s1, red) * inv_n;
+    const float m2 = block_sum(s2, red) * inv_n;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int64_t i = lo + 4 * lane + 128 * u;
+        if (i < hi) {
+            const float4 h = sx[32 * u];
+            float4 o;
+            o.x = rstd * (v[u].x - m1 - h.x * m2);
+            o.y = rstd * (v[u].y - m1 - h.y * m2);
+            o.z = rstd * (v[u].z - m1 - h.z * m2);
+            o.w = rstd * (v[u].w - m1 - h.w * m2);
+            *reinterpret_cast<float4*>(dx + base + i) = o;
+        }
+    }
+}
+
 // smallest cluster size whose largest per-CTA share, times `copies` staged floats per element, fits the budget; 0 = none
 static int norm_cluster_size(int cpg, int64_t HW, int copies, int max_cl, int64_t* max_share) {
     for (int cl = 1; cl <= max_cl; cl *= 2) {
@@ -575,8 +672,9 @@ static int norm_cluster_size(int cpg, int64_t HW, int copies, int max_cl, int64_
 // vqb_tune "norm_cluster": 0 = the round-1 one-CTA-per-group staged kernels only; 1 = product (register-resident backward,
 // small-share kernels for groups that fit 40 KB); 2 = also clusters of 2-8 CTAs per group (measured slower)
 VQB_KNOB g_norm_cluster = 1;
+VQB_KNOB g_norm_bwd2 = 1;  // vqb_tune "norm_bwd2": 1 (default) = the two-CTAs-per-SM variant of the register-resident backward
 #ifdef VQB_EXPERIMENTAL
-void set_norm_cluster(int v) { g_norm_cluster = v; }
+void set_norm_cluster(int v) { if (v >= 16) g_norm_bwd2 = v - 16; else g_norm_cluster = v; }
 #endif
 
 template <typename Kern, typename... Args>
@@ -674,8 +772,15 @@ extern "C" int vqb_groupnorm_silu_backward_f32(const float* dy, const float* x, 
     const int64_t items = (int64_t)(C / groups) * ((HW + kNormSeg - 1) / kNormSeg);
     if (g_norm_cluster == 1 && items <= kNormRegItems && HW % 4 == 0 && n >= 8192 &&
         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0) {
-        groupnorm_silu_bwd_reg_kernel<<<blocks, kNormThreads, 0, s>>>(dy, x, gamma, beta, mean, rstd, C, HW, groups, dx,
-                                                                     dgamma_accum, dbeta_accum);
+        if (g_norm_bwd2) {
+            constexpr int kSm = kNormThreads * 8 * 16;  // 64 KB
+            VQB_CUDA_TRY(cudaFuncSetAttribute(groupnorm_silu_bwd_reg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSm));
+            groupnorm_silu_bwd_reg2_kernel<<<blocks, kNormThreads, kSm, s>>>(dy, x, gamma, beta, mean, rstd, C, HW, groups, dx,
+                                                                            dgamma_accum, dbeta_accum);
+        } else {
+            groupnorm_silu_bwd_reg_kernel<<<blocks, kNormThreads, 0, s>>>(dy, x, gamma, beta, mean, rstd, C, HW, groups, dx,
+                                                                         dgamma_accum, dbeta_accum);
+        }
     } else if (cl > 0 && B * (int64_t)groups * cl < (1LL << 31)) {
         const size_t smem = sizeof(float) * (size_t)(2 * share);
 #define VQB_NORM_BWD(c)                                                                                                  \
