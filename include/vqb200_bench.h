@@ -27,6 +27,7 @@ extern "C" {
  *   "tc16_group"         0|4|8  codes per candidate group of the fp16 tensor search (0 = 8 up to padded D 128, 4 above)
  *   "dw_hw_trunc"        0|1    1x1 conv parameter gradients: 1 = the landed fp32 tile is the hi image as it is (relies on the
  *                               tensor core ignoring the low 13 mantissa bits), only the residual image is written
+ *   "norm_fwd_reg"       0|1    GroupNorm+SiLU forward (<= 16 items per group): staged in shared memory / register-resident (default 1)
  *   "norm_bwd2"          0|1    GroupNorm+SiLU backward (<= 16 items per group): one 512-thread CTA per SM with xhat and dxhat in
  *                               registers / two per SM with xhat in shared memory (default 1)
  *   "norm_cluster"       0|1|2  GroupNorm+SiLU: round-1 staged kernels only / product (default 1) / also clusters of

@@ -35,6 +35,13 @@ for B, C, H, W, mode in [(b, c, h, w, m) for (b, c, h, w) in ((64, 512, 32, 32),
     tt = timed(lambda: F.silu(F.group_norm(x, 32, w, b, 1e-6)))
     y, mean, rstd = ops.groupnorm_silu(x, w, b, 32, 1e-6)
     tb = timed(lambda: ops.groupnorm_silu_backward(gy, x, w, b, mean, rstd, 32))
+    if mode == 1:  # A/B of the forward: register-resident (default) vs staged in shared memory (norm_fwd_reg 0)
+        y1 = ops.groupnorm_silu(x, w, b, 32, 1e-6)[0]
+        _cabi.check(lib.vqb_tune(b"norm_fwd_reg", 0), "t")
+        tf0 = timed(lambda: ops.groupnorm_silu(x, w, b, 32, 1e-6))
+        y0 = ops.groupnorm_silu(x, w, b, 32, 1e-6)[0]
+        _cabi.check(lib.vqb_tune(b"norm_fwd_reg", 1), "t")
+        print(f"[{B},{C},{H},{W}] forward: register-resident (product) {tf:.3f} ms vs staged {tf0:.3f} ms; max |dy| {float((y0 - y1).abs().max()):.2e}", flush=True)
     if mode == 1:  # A/B of the register-resident backward: one CTA per SM (norm_bwd2 0) vs two (default)
         d1 = ops.groupnorm_silu_backward(gy, x, w, b, mean, rstd, 32)[0]
         _cabi.check(lib.vqb_tune(b"norm_bwd2", 0), "t")

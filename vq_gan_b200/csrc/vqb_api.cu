@@ -111,6 +111,10 @@ extern "C" int vqb_tune(const char* key, int value) {
         set_dw_hw_trunc(value);
         return VQB_OK;
     }
+    if (strcmp(key, "norm_fwd_reg") == 0 && (value == 0 || value == 1)) {
+        set_norm_cluster(32 + value);
+        return VQB_OK;
+    }
     if (strcmp(key, "norm_bwd2") == 0 && (value == 0 || value == 1)) {
         set_norm_cluster(16 + value);
         return VQB_OK;
