@@ -67,3 +67,26 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_cabi, "LIB_PATH", "/nonexistent/libvqb200.so")
     with pytest.raises(_cabi.VqbError, match="no CPU or eager fallback"):
         _cabi.lib()
+
+
+def test_round2_host_side_queries_without_gpu():
+    """Pure host arithmetic of the entry points added in round 2: which shapes the 1x1 convolution's parameter-gradient
+    kernel takes, and that the search workspace / codebook pack grow by the pruned exact tier / the duplicate table
+    exactly where those apply."""
+    lib = vq_gan_b200.lib()
+    assert lib.vqb_conv1x1_dw_supported(256, 256, 1024) == 1
+    assert lib.vqb_conv1x1_dw_supported(16, 1, 32) == 1
+    assert lib.vqb_conv1x1_dw_supported(24, 64, 1024) == 0      # Cin % 16
+    assert lib.vqb_conv1x1_dw_supported(64, 257, 1024) == 0     # Cout > 256
+    assert lib.vqb_conv1x1_dw_supported(64, 64, 1022) == 0      # HW % 4
+    assert lib.vqb_conv1x1_dw_supported(64, 64, 16) == 0        # HW < 32
+    f16 = _cabi.ALGO_TCGEN05_F16
+    # pruned tier: 2048 <= K <= 16384 only
+    small = lib.vqb_search_workspace_bytes(64, 256, 1024, 1024, f16)
+    mid = lib.vqb_search_workspace_bytes(64, 256, 1024, 4096, f16)
+    big = lib.vqb_search_workspace_bytes(64, 256, 1024, 32768, f16)
+    assert mid > small and mid > big and small == big
+    # duplicate table only with the fp16 image (D > 16)
+    low = lib.vqb_codebook_pack_bytes(4096, 4)
+    high = lib.vqb_codebook_pack_bytes(4096, 64)
+    assert high - low > 8 * 2 * 4096          # at least the 2 * Kpad 64-bit slots
