@@ -104,7 +104,7 @@ extern "C" int vqb_tune(const char* key, int value) {
         return VQB_OK;
     }
     if (strcmp(key, "tc16_branchy") == 0 && (value == 0 || value == 1)) {
-        set_tc16_cluster(16 + value);
+        set_tc16_branchy(value);
         return VQB_OK;
     }
     if (strcmp(key, "dw_hw_trunc") == 0 && (value == 0 || value == 1)) {
@@ -112,11 +112,11 @@ extern "C" int vqb_tune(const char* key, int value) {
         return VQB_OK;
     }
     if (strcmp(key, "norm_fwd_reg") == 0 && (value == 0 || value == 1)) {
-        set_norm_cluster(32 + value);
+        set_norm_fwd_reg(value);
         return VQB_OK;
     }
     if (strcmp(key, "norm_bwd2") == 0 && (value == 0 || value == 1)) {
-        set_norm_cluster(16 + value);
+        set_norm_bwd2(value);
         return VQB_OK;
     }
     if (strcmp(key, "norm_cluster") == 0 && value >= 0 && value <= 2) {
@@ -124,11 +124,11 @@ extern "C" int vqb_tune(const char* key, int value) {
         return VQB_OK;
     }
     if (strcmp(key, "tc16_pruned") == 0 && (value == 0 || value == 1)) {
-        set_tc16_cluster(64 + value);
+        set_tc16_pruned(value);
         return VQB_OK;
     }
     if (strcmp(key, "tc16_group") == 0 && (value == 0 || value == 4 || value == 8)) {
-        set_tc16_cluster(32 + value);
+        set_tc16_group(value);
         return VQB_OK;
     }
     if (strcmp(key, "tc16_cluster") == 0 && (value == 1 || value == 2 || value == 4)) {

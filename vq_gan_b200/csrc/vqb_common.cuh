@@ -239,7 +239,12 @@ int launch_search_tc16(const float* z, int64_t B, int D, int64_t HW, const float
 void tc16_split_pointers(void* ws, int64_t N, int D, __half** z16, float** inv_scale, float** znorm, float** zres);
 void set_lowd_variant(int v);
 void set_tc16_cluster(int c);
+void set_tc16_branchy(int v);
+void set_tc16_group(int v);
+void set_tc16_pruned(int v);
 void set_norm_cluster(int v);
+void set_norm_bwd2(int v);
+void set_norm_fwd_reg(int v);
 void set_dw_hw_trunc(int v);
 
 }  // namespace vqb

@@ -740,7 +740,9 @@ VQB_KNOB g_norm_cluster = 1;
 VQB_KNOB g_norm_fwd_reg = 1;  // vqb_tune "norm_fwd_reg": 1 (default) = register-resident forward for groups of at most 16 items
 VQB_KNOB g_norm_bwd2 = 1;  // vqb_tune "norm_bwd2": 1 (default) = the two-CTAs-per-SM variant of the register-resident backward
 #ifdef VQB_EXPERIMENTAL
-void set_norm_cluster(int v) { if (v >= 32) g_norm_fwd_reg = v - 32; else if (v >= 16) g_norm_bwd2 = v - 16; else g_norm_cluster = v; }
+void set_norm_cluster(int v) { g_norm_cluster = v; }
+void set_norm_bwd2(int v) { g_norm_bwd2 = v; }
+void set_norm_fwd_reg(int v) { g_norm_fwd_reg = v; }
 #endif
 
 template <typename Kern, typename... Args>

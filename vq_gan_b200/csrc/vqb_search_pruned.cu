@@ -593,7 +593,7 @@ int launch_search_pruned(const float* z, int64_t B, int D, int64_t HW, const flo
     const int64_t N = B * HW;
     const int sms = sm_count();
     const PrunedWorkspace w = pruned_workspace(N, K, D, kPrMaxSms);
-    if (!pruned_eligible(K, D) || !ws || ws_bytes < w.total || sms > kPrMaxSms) {
+    if (!pruned_eligible(K, D) || !ws || ws_bytes < w.total) {
         set_error("pruned exact tier: not eligible or workspace too small (%zu < %zu)", ws_bytes, w.total);
         return VQB_ERR_WORKSPACE;
     }
@@ -627,7 +627,8 @@ int launch_search_pruned(const float* z, int64_t B, int D, int64_t HW, const flo
     VQB_LAUNCH_CHECK("pruned_select_kernel");
     pruned_scatter_kernel<<<sms * 2, 256, 0, s>>>(K, w.n_tiles, list_count, header, counts, cursors, mask, lists, state);
     VQB_LAUNCH_CHECK("pruned_scatter_kernel");
-    pruned_search_kernel<<<sms * 2, kPrThreads, 0, s>>>(z, D, HW, K, w.n_tiles, token_list, list_count, header, state, counts,
+    const int search_ctas = 2 * (sms < kPrMaxSms ? sms : kPrMaxSms);  // one scratch slice per CTA (workspace sized for kPrMaxSms)
+    pruned_search_kernel<<<search_ctas, kPrThreads, 0, s>>>(z, D, HW, K, w.n_tiles, token_list, list_count, header, state, counts,
                                                        lists, mask, Es, hs, perm, scratch, idx_out, dmin_out);
     VQB_LAUNCH_CHECK("pruned_search_kernel");
     *remaining = state + 1;

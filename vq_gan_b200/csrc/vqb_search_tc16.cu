@@ -748,9 +748,10 @@ VQB_KNOB g_tc16_branchy = 0;  // vqb_tune "tc16_branchy": conditional top-4 inse
 VQB_KNOB g_tc16_pruned = 1;   // vqb_tune "tc16_pruned": 0 = no pruned exact tier (A/B)
 VQB_KNOB g_tc16_group = 0;    // vqb_tune "tc16_group": 0 = tc16_group_size(Dpad), 4 or 8 = forced (cluster 2, Dpad <= 256)
 #ifdef VQB_EXPERIMENTAL
-void set_tc16_cluster(int c) {
-    if (c >= 64) g_tc16_pruned = c - 64; else if (c >= 32) g_tc16_group = c - 32; else if (c >= 16) g_tc16_branchy = c - 16; else g_tc16_cluster = c;
-}
+void set_tc16_cluster(int c) { g_tc16_cluster = c; }
+void set_tc16_branchy(int v) { g_tc16_branchy = v; }
+void set_tc16_group(int v) { g_tc16_group = v; }
+void set_tc16_pruned(int v) { g_tc16_pruned = v; }
 #endif
 
 // codes per candidate group: 8 where the epilogue, not the tensor pipe, bounds the kernel (see search_tc16_kernel)
