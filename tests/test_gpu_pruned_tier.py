@@ -109,3 +109,39 @@ def test_nan_and_inf_tokens_and_module_forward():
     assert rep["outside"] == 0, rep
     fo = orc.forward(zi, E, 0.25, idx=indices.reshape(-1).cpu())
     assert torch.equal(z_q.detach().cpu(), fo["z_q"])
+
+
+def test_cuda_graph_replay_with_the_tier_inside():
+    """The tier decides everything on the device, so a captured forward replays correctly whether the data make it run
+    (collapsed codebook), decline, or stay idle (healthy codebook) -- one graph, three codebooks."""
+    from vq_gan_b200 import VectorQuantizer
+    from vq_gan_b200.graphs import GraphedVectorQuantizer
+    K, D, B, H = 4096, 64, 16, 32
+    torch.manual_seed(3)
+    vq = VectorQuantizer(K, D, 0.25, lazy_stats=True).cuda()
+    gvq = GraphedVectorQuantizer(vq, torch.randn(B, D, H, H, device="cuda", requires_grad=True))
+    z_c, E_c = _collapsed(K, D, 8, 1e-4, B * H * H, 0.05, seed=11)
+    z_1, E_1 = _collapsed(K, D, 1, 1e-4, B * H * H, 0.05, seed=12)
+    cases = ((z_c, E_c, "taken"), (z_1, E_1, "declined"), (torch.randn(B * H * H, D), torch.randn(K, D), "idle"))
+    for z_rows, E, what in cases:
+        with torch.no_grad():
+            vq.embedding.weight.copy_(E)
+        z = _as_images(z_rows, H * H).view(B, D, H, H).cuda()
+        g = torch.randn(B, D, H, H, device="cuda")
+        outs = []
+        for mod in (vq, gvq):
+            zc = z.clone().requires_grad_(True)
+            vq.embedding.weight.grad = None
+            z_q, ld, idx = mod(zc)
+            torch.autograd.backward((z_q, ld["vq_loss"]), (g, torch.ones((), device="cuda")))
+            outs.append((z_q.detach().clone(), idx.clone(), zc.grad.clone(), vq.last_search_stats.tolist()))
+        e, r = outs
+        assert torch.equal(e[0], r[0]) and torch.equal(e[1], r[1]) and torch.equal(e[2], r[2]), what
+        st = e[3]
+        assert st[1] == 4, st
+        if what == "taken":
+            assert st[3] == st[0] > 0, st
+        elif what == "declined":
+            assert st[3] == 0 and st[0] > 0.9 * B * H * H, st
+        else:
+            assert st[3] == 0 and st[0] < 0.01 * B * H * H, st
