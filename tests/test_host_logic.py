@@ -162,3 +162,20 @@ def test_loss_dict_is_a_dict_of_floats_on_every_read_path():
     d = fresh()
     d["codebook_loss"] = 9.0
     assert d["codebook_loss"] == 9.0 and d["commitment_loss"] == 0.5
+
+
+def test_round2_ops_reject_cpu_tensors():
+    """No CPU path exists for the layers next to the quantizer either: host tensors raise instead of being emulated."""
+    from vq_gan_b200 import GroupNormSiLU, QuantConv1x1, ops
+    x = torch.randn(2, 32, 8, 8)
+    gy = torch.randn(2, 16, 8, 8)
+    with pytest.raises(RuntimeError):
+        ops.conv1x1_param_grads(gy, x)
+    with pytest.raises(RuntimeError):
+        ops.conv1x1(x, torch.randn(16, 32), None)
+    with pytest.raises(RuntimeError):
+        ops.groupnorm_silu(x, torch.ones(32), torch.zeros(32), 4, 1e-6)
+    with pytest.raises(RuntimeError):
+        QuantConv1x1(32, 16)(x)
+    with pytest.raises(RuntimeError):
+        GroupNormSiLU(4, 32)(x)
